@@ -1,0 +1,758 @@
+// hsr_api.cu — host side of the C-ABI in include/hsrans_b200.h: header validation, the mt_ block index,
+// sharding, device contexts, the host<->device pipeline and the kernel launches.
+//
+// Mirrors the framing logic of the reference's decode entry points (error returns included):
+//   raw    src/rANS32x32_16w.cpp:161-201          block_  src/block_rANS32x32_16w_decode.cpp:18-96
+//   mt_    src/mt_rANS32x64_16w_decode.cpp:12-97  (the serial header walk of :40-66,94 becomes hsr_mt_index)
+// There is no CPU decode path in this file: without a CUDA device every compute entry point fails.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "hsr_kernels.cuh"
+
+using namespace hsr;
+
+// ------------------------------------------------------------------------------------------------ errors / options
+
+static thread_local std::string g_err;
+
+static void set_err(const char *fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+#define CU_TRY(call, onfail)                                                                              \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) {                                                                              \
+      set_err("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);               \
+      (void)cudaGetLastError();                                                                           \
+      onfail;                                                                                             \
+    }                                                                                                     \
+  } while (0)
+
+static std::atomic<long> g_optTable{0}, g_optWarps{0}, g_optChunkMb{0};
+
+extern "C" int hsr_version(void) { return HSR_VERSION; }
+
+extern "C" const char *hsr_last_error(void) { return g_err.c_str(); }
+
+extern "C" int hsr_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int hsr_set_device(int device)
+{
+  CU_TRY(cudaSetDevice(device), return -1);
+  return 0;
+}
+
+extern "C" int hsr_set_option(const char *key, long value)
+{
+  if (!key) return -1;
+  if (!strcmp(key, "table")) { if (value < 0 || value > 2) return -1; g_optTable = value; return 0; }
+  if (!strcmp(key, "warps")) { if (value < 0 || value > 16) return -1; g_optWarps = value; return 0; }
+  if (!strcmp(key, "chunk_mb")) { if (value < 0) return -1; g_optChunkMb = value; return 0; }
+  return -1;
+}
+
+extern "C" long hsr_get_option(const char *key)
+{
+  if (!key) return -1;
+  if (!strcmp(key, "table")) return g_optTable;
+  if (!strcmp(key, "warps")) return g_optWarps;
+  if (!strcmp(key, "chunk_mb")) return g_optChunkMb;
+  return -1;
+}
+
+extern "C" size_t hsr_capacity(int N, size_t inputSize)
+{
+  // src/rANS32x32_16w.cpp:10-13: buffer + histogram + state (+ one row of slack)
+  return inputSize + (size_t)N + sizeof(uint16_t) * 256 + sizeof(uint32_t) * (size_t)N + sizeof(uint64_t) * 2;
+}
+
+extern "C" void *hsr_host_alloc(size_t bytes)
+{
+  void *p = nullptr;
+  CU_TRY(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable), return nullptr);
+  return p;
+}
+
+extern "C" void hsr_host_free(void *p)
+{
+  if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------------------------------------ header + index
+
+static inline uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+struct Header {
+  uint64_t n, compLen;
+};
+
+static bool valid_codec(int family, int N, int bits)
+{
+  return family >= HSR_RAW && family <= HSR_MT && (N == 32 || N == 64) && bits >= 10 && bits <= 15;
+}
+
+// the checks every reference decoder starts with (src/rANS32x32_16w.cpp:164-180)
+static bool read_header(int N, const uint8_t *in, size_t inLength, size_t outCapacity, Header *h)
+{
+  if (!in || inLength < 16 + 4 * (size_t)N + 512) { set_err("input shorter than the fixed header"); return false; }
+  h->n = rd64(in);
+  h->compLen = rd64(in + 8);
+  if (h->n > outCapacity) { set_err("decoded length %llu exceeds outCapacity %zu", (unsigned long long)h->n, outCapacity); return false; }
+  if (inLength < h->compLen) { set_err("inLength %zu < compressed length %llu", inLength, (unsigned long long)h->compLen); return false; }
+  if (h->n < (uint64_t)N) { set_err("decoded length below the state count is undefined in the reference"); return false; }
+  return true;
+}
+
+constexpr uint64_t kFillUnit = 4ull << 20; // single-symbol runs are cut into fills of this size
+constexpr uint64_t kMaxUnitIn = 0xfff00000ull; // per-unit compressed bytes must fit the ring's 32-bit cursor
+
+extern "C" long hsr_mt_index(int N, const uint8_t *in, size_t inLength, hsr_block_t *blocks, size_t maxBlocks)
+{
+  if (!(N == 32 || N == 64)) { set_err("state count must be 32 or 64"); return -1; }
+  if (!in || inLength < 16 + 4 * (size_t)N + 512) { set_err("input shorter than the fixed header"); return -1; }
+  const uint64_t n = rd64(in);
+  if (n < (uint64_t)N) { set_err("decoded length below the state count"); return -1; }
+  const uint64_t outLengthInStates = n - N + 1;
+  uint64_t pos = 16, i = 0;
+  size_t count = 0;
+  long lastCoded = -1;
+  auto emit = [&](const hsr_block_t &b) {
+    if (blocks && count < maxBlocks) blocks[count] = b;
+    count++;
+  };
+  do {
+    if (pos + 8 > inLength) { set_err("mt_ chain runs past the input at offset %llu", (unsigned long long)pos); return -1; }
+    const uint64_t v = rd64(in + pos);
+    if (v >> 63) { // single-symbol run (src/mt_rANS32x64_16w_decode.cpp:46-54)
+      const uint64_t size = v & ((1ull << 54) - 1);
+      if (size > n - i) { set_err("single-symbol run overruns the decoded length"); return -1; }
+      for (uint64_t o = 0; o < size; o += kFillUnit) {
+        hsr_block_t b{};
+        b.inOffset = pos; b.inEnd = pos + 8; b.outOffset = i + o; b.count = std::min(kFillUnit, size - o);
+        b.kind = 1; b.symbol = (uint32_t)(v >> 54) & 0xffu;
+        emit(b);
+      }
+      pos += 8;
+      i += size;
+    } else {
+      if (pos + 16 + 4 * (uint64_t)N + 512 > inLength) { set_err("mt_ block header runs past the input"); return -1; }
+      const uint64_t skip = rd64(in + pos + 8);
+      if (skip >= (inLength - (pos + 16)) / 2) { set_err("mt_ skip offset runs past the input"); return -1; }
+      const uint64_t after = pos + 16 + 2 * (skip + 1); // :59
+      if (after < pos + 16 + 4 * (uint64_t)N + 512 || after > inLength) { set_err("mt_ skip offset inconsistent"); return -1; }
+      if (after - pos > kMaxUnitIn) { set_err("mt_ block larger than 4 GiB compressed is not supported"); return -1; }
+      uint64_t end = i + v; // :77-82
+      if (end > outLengthInStates) end = outLengthInStates;
+      else if (end & (uint64_t)(N - 1)) { set_err("mt_ block end not a multiple of the state count"); return -1; }
+      const uint64_t rows = end > i ? (end - i + N - 1) / N : 0;
+      hsr_block_t b{};
+      b.inOffset = pos + 16; b.inEnd = after; b.outOffset = i; b.count = rows * N; b.kind = 0;
+      lastCoded = (long)count;
+      emit(b);
+      pos = after;
+      i += rows * N;
+    }
+  } while (i < outLengthInStates);
+
+  if (i < n) { // leftover < N symbols use the last coded block's states and cursor (:99-130)
+    if (lastCoded < 0 || (size_t)lastCoded + 1 != count) { set_err("mt_ stream ends in a tail without a coded block"); return -1; }
+    if (blocks && (size_t)lastCoded < maxBlocks) {
+      blocks[lastCoded].tail = (uint32_t)(n - i);
+      blocks[lastCoded].count += n - i;
+    }
+  }
+  return (long)count;
+}
+
+extern "C" int hsr_mt_partition(const hsr_block_t *blocks, size_t count, int parts, size_t *firstUnit)
+{
+  if (!blocks || parts < 1 || !firstUnit) return -1;
+  uint64_t total = 0;
+  for (size_t k = 0; k < count; k++) total += (blocks[k].inEnd - blocks[k].inOffset) + blocks[k].count;
+  size_t k = 0;
+  uint64_t acc = 0;
+  firstUnit[0] = 0;
+  for (int p = 1; p < parts; p++) {
+    const uint64_t target = total / parts * p + (total % parts) * p / parts;
+    while (k < count && acc + ((blocks[k].inEnd - blocks[k].inOffset) + blocks[k].count) / 2 <= target) {
+      acc += (blocks[k].inEnd - blocks[k].inOffset) + blocks[k].count;
+      k++;
+    }
+    firstUnit[p] = k;
+  }
+  firstUnit[parts] = count;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel launch
+
+static int pick_table(int bits)
+{
+  const long opt = g_optTable;
+  if (opt == 1) return TK_RANK;
+  if (opt == 2) return bits <= 12 ? TK_PACKED : TK_RANK;
+  return bits <= 12 ? TK_PACKED : TK_RANK;
+}
+
+static const KernelEntry &kernel_entry(int N, int bits, int table) { return (N == 32 ? kKernels32 : kKernels64)[bits - 10][table - 1]; }
+
+struct LaunchInfo {
+  int ctasPerSm = 0, smCount = 0;
+};
+
+static std::mutex g_attrMutex;
+
+// opt in to > 48 KB dynamic shared memory and query residency, once per (kernel, device)
+static bool prepare_kernel(const void *fn, int smemBytes, int threads, LaunchInfo *li)
+{
+  struct Key { const void *fn; int dev; int smem; LaunchInfo li; };
+  static std::vector<Key> cache;
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev), return false);
+  std::lock_guard<std::mutex> lock(g_attrMutex);
+  for (auto &k : cache)
+    if (k.fn == fn && k.dev == dev && k.smem == smemBytes) { *li = k.li; return true; }
+  CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes), return false);
+  CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), return false);
+  LaunchInfo out;
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out.ctasPerSm, fn, threads, smemBytes), return false);
+  CU_TRY(cudaDeviceGetAttribute(&out.smCount, cudaDevAttrMultiProcessorCount, dev), return false);
+  if (out.ctasPerSm < 1) { set_err("kernel does not fit on an SM with %d bytes of shared memory", smemBytes); return false; }
+  cache.push_back({fn, dev, smemBytes, out});
+  *li = out;
+  return true;
+}
+
+// launches the units kernel over blocks [first, first+count) of a device-resident index
+static int launch_units(int N, int bits, const uint8_t *dIn, uint64_t inBase, uint8_t *dOut, uint64_t outBase,
+                        const hsr_block_t *dBlocks, uint32_t numBlocks, uint32_t *dCounter, cudaStream_t st)
+{
+  if (numBlocks == 0) return 0;
+  const int table = pick_table(bits);
+  const KernelEntry &ke = kernel_entry(N, bits, table);
+  DecodeParams p{dIn, inBase, dOut, outBase, dBlocks, numBlocks, dCounter};
+  void *args[] = {&p};
+  CU_TRY(cudaMemsetAsync(dCounter, 0, 4, st), return -1); // work counter only; status bits accumulate
+  LaunchInfo li;
+  if (numBlocks == 1) {
+    if (!prepare_kernel(ke.unitsW1, ke.warpBytes, 32, &li)) return -1;
+    CU_TRY(cudaLaunchKernel(ke.unitsW1, dim3(1), dim3(32), args, (size_t)ke.warpBytes, st), return -1);
+    return 1;
+  }
+  const int warps = 4;
+  const int smem = ke.warpBytes * warps;
+  if (!prepare_kernel(ke.unitsW4, smem, warps * 32, &li)) return -1;
+  const uint32_t want = (numBlocks + warps - 1) / warps;
+  const uint32_t grid = std::min<uint32_t>(want, (uint32_t)(li.ctasPerSm * li.smCount));
+  CU_TRY(cudaLaunchKernel(ke.unitsW4, dim3(grid), dim3(warps * 32), args, (size_t)smem, st), return -1);
+  return 1;
+}
+
+static int launch_block_stream(int N, int bits, const uint8_t *dIn, uint64_t inLength, uint8_t *dOut, uint64_t n,
+                               uint32_t *dCounter, cudaStream_t st)
+{
+  const int table = pick_table(bits);
+  const KernelEntry &ke = kernel_entry(N, bits, table);
+  BlockStreamParams p{dIn, inLength, dOut, n, dCounter};
+  void *args[] = {&p};
+  LaunchInfo li;
+  if (!prepare_kernel(ke.block, ke.warpBytes, 32, &li)) return -1;
+  CU_TRY(cudaLaunchKernel(ke.block, dim3(1), dim3(32), args, (size_t)ke.warpBytes, st), return -1);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------ device mt_ walk
+
+// Serial walk of the mt_ chain for streams that only exist in device memory. One warp: lanes 0..7 fetch the
+// eight u16 of {size, skip} in one round trip per hop. Emits the same records as hsr_mt_index.
+__global__ void mt_walk_kernel(const uint8_t *in, uint64_t inLength, uint32_t N, hsr_block_t *blocks, uint64_t maxBlocks,
+                               unsigned long long *result /* [0] count, [1] error */)
+{
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t n = ldg_u64_a2(in);
+  uint64_t err = 0, count = 0, pos = 16, i = 0;
+  long long lastCoded = -1;
+  if (n < N) err = 1;
+  const uint64_t outLengthInStates = n - N + 1;
+  while (!err) {
+    if (pos + 8 > inLength) { err = 2; break; }
+    uint32_t h = 0;
+    if (lane < 8 && pos + 2 * lane + 2 <= inLength) h = ldg_u16(in + pos + 2 * lane);
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) w[k] = __shfl_sync(kFull, h, k);
+    const uint64_t v = (uint64_t)w[0] | ((uint64_t)w[1] << 16) | ((uint64_t)w[2] << 32) | ((uint64_t)w[3] << 48);
+    const uint64_t skip = (uint64_t)w[4] | ((uint64_t)w[5] << 16) | ((uint64_t)w[6] << 32) | ((uint64_t)w[7] << 48);
+    if (v >> 63) {
+      const uint64_t size = v & ((1ull << 54) - 1);
+      if (size > n - i) { err = 3; break; }
+      for (uint64_t o = 0; o < size; o += kFillUnit) {
+        if (lane == 0 && count < maxBlocks) {
+          hsr_block_t b{};
+          b.inOffset = pos; b.inEnd = pos + 8; b.outOffset = i + o; b.count = size - o < kFillUnit ? size - o : kFillUnit;
+          b.kind = 1; b.symbol = (uint32_t)(v >> 54) & 0xffu;
+          blocks[count] = b;
+        }
+        count++;
+      }
+      pos += 8;
+      i += size;
+    } else {
+      if (pos + 16 + 4ull * N + 512 > inLength) { err = 4; break; }
+      if (skip >= (inLength - (pos + 16)) / 2) { err = 5; break; }
+      const uint64_t after = pos + 16 + 2 * (skip + 1);
+      if (after < pos + 16 + 4ull * N + 512 || after > inLength || after - pos > kMaxUnitIn) { err = 6; break; }
+      uint64_t end = i + v;
+      if (end > outLengthInStates) end = outLengthInStates;
+      else if (end & (uint64_t)(N - 1)) { err = 7; break; }
+      const uint64_t rows = end > i ? (end - i + N - 1) / N : 0;
+      if (lane == 0 && count < maxBlocks) {
+        hsr_block_t b{};
+        b.inOffset = pos + 16; b.inEnd = after; b.outOffset = i; b.count = rows * N; b.kind = 0;
+        blocks[count] = b;
+      }
+      lastCoded = (long long)count;
+      count++;
+      pos = after;
+      i += rows * N;
+    }
+    if (!(i < outLengthInStates)) break;
+  }
+  if (!err && i < n) {
+    if (lastCoded < 0 || (uint64_t)lastCoded + 1 != count) err = 8;
+    else if (lane == 0 && (uint64_t)lastCoded < maxBlocks) {
+      blocks[lastCoded].tail = (uint32_t)(n - i);
+      blocks[lastCoded].count += n - i;
+    }
+  }
+  if (lane == 0) { result[0] = count; result[1] = err; }
+}
+
+// ------------------------------------------------------------------------------------------------ prepared streams
+
+struct hsr_stream {
+  int family = 0, N = 0, bits = 0, device = 0;
+  uint64_t n = 0, compLen = 0;
+  uint8_t *dIn = nullptr;   // device bytes of [inBase, inBase + inBytes)
+  bool ownsIn = false;
+  uint64_t inBase = 0, inBytes = 0;
+  std::vector<hsr_block_t> blocks; // this shard's units (absolute offsets)
+  hsr_block_t *dBlocks = nullptr;
+  uint32_t *dCounter = nullptr;    // [0] work counter, [1] status
+  uint64_t outOffset = 0, outBytes = 0;
+  double indexMs = 0;
+};
+
+static void stream_release(hsr_stream *s)
+{
+  if (!s) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(s->device);
+  if (s->ownsIn && s->dIn) cudaFree(s->dIn);
+  if (s->dBlocks) cudaFree(s->dBlocks);
+  if (s->dCounter) cudaFree(s->dCounter);
+  cudaSetDevice(prev);
+  delete s;
+}
+
+extern "C" void hsr_stream_free(hsr_stream_t *s) { stream_release(s); }
+
+static bool stream_finish(hsr_stream *s) // uploads the index, allocates the counters
+{
+  CU_TRY(cudaMalloc(&s->dCounter, 16), return false);
+  CU_TRY(cudaMemset(s->dCounter, 0, 16), return false);
+  if (!s->blocks.empty()) {
+    CU_TRY(cudaMalloc(&s->dBlocks, s->blocks.size() * sizeof(hsr_block_t)), return false);
+    CU_TRY(cudaMemcpy(s->dBlocks, s->blocks.data(), s->blocks.size() * sizeof(hsr_block_t), cudaMemcpyHostToDevice), return false);
+  }
+  return true;
+}
+
+static hsr_block_t raw_unit(int N, const Header &h)
+{
+  hsr_block_t b{};
+  b.inOffset = 16; // u16 counts[256], then u32 states[N], then words (src/rANS32x32_16w.cpp:183-200)
+  b.inEnd = h.compLen;
+  b.outOffset = 0;
+  b.count = h.n;
+  b.kind = 2;
+  b.tail = (uint32_t)(h.n % (uint64_t)N);
+  return b;
+}
+
+extern "C" hsr_stream_t *hsr_stream_upload(int family, int N, int bits, const uint8_t *in, size_t inLength, int shard, int shards)
+{
+  g_err.clear();
+  if (!valid_codec(family, N, bits)) { set_err("unsupported codec (family %d, N %d, bits %d)", family, N, bits); return nullptr; }
+  if (shards < 1 || shard < 0 || shard >= shards) { set_err("bad shard %d of %d", shard, shards); return nullptr; }
+  if (family != HSR_MT && shards != 1) { set_err("only mt_ streams shard; raw and block_ are one recurrence"); return nullptr; }
+  Header h;
+  if (!read_header(N, in, inLength, (size_t)-1, &h)) return nullptr;
+  if (h.compLen < 16 + 4 * (uint64_t)N + 512) { set_err("compressed length field too small"); return nullptr; }
+
+  std::unique_ptr<hsr_stream, void (*)(hsr_stream *)> s(new hsr_stream, stream_release);
+  s->family = family; s->N = N; s->bits = bits; s->n = h.n; s->compLen = h.compLen;
+  CU_TRY(cudaGetDevice(&s->device), return nullptr);
+
+  uint64_t lo = 0, hi = h.compLen;
+  if (family == HSR_MT) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const long cnt = hsr_mt_index(N, in, (size_t)h.compLen, nullptr, 0);
+    if (cnt < 0) return nullptr;
+    std::vector<hsr_block_t> all((size_t)cnt);
+    if (hsr_mt_index(N, in, (size_t)h.compLen, all.data(), all.size()) != cnt) return nullptr;
+    s->indexMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::vector<size_t> first((size_t)shards + 1);
+    hsr_mt_partition(all.data(), all.size(), shards, first.data());
+    s->blocks.assign(all.begin() + first[shard], all.begin() + first[shard + 1]);
+    if (!s->blocks.empty()) {
+      lo = s->blocks.front().inOffset & ~15ull;
+      hi = s->blocks.back().inEnd;
+      s->outOffset = s->blocks.front().outOffset;
+      s->outBytes = s->blocks.back().outOffset + s->blocks.back().count - s->outOffset;
+    } else {
+      lo = hi = 0;
+    }
+  } else {
+    if (family == HSR_RAW) {
+      if (h.compLen > kMaxUnitIn) { set_err("raw streams above 4 GiB compressed are not supported"); return nullptr; }
+      s->blocks.push_back(raw_unit(N, h));
+    }
+    s->outOffset = 0;
+    s->outBytes = h.n;
+  }
+  s->inBase = lo;
+  s->inBytes = hi - lo;
+  if (s->inBytes) {
+    CU_TRY(cudaMalloc(&s->dIn, (size_t)s->inBytes + 16), return nullptr);
+    s->ownsIn = true;
+    CU_TRY(cudaMemcpy(s->dIn, in + lo, (size_t)s->inBytes, cudaMemcpyHostToDevice), return nullptr);
+  }
+  if (!stream_finish(s.get())) return nullptr;
+  return s.release();
+}
+
+extern "C" hsr_stream_t *hsr_stream_from_device(int family, int N, int bits, const void *dInV, size_t inLength)
+{
+  g_err.clear();
+  if (!valid_codec(family, N, bits)) { set_err("unsupported codec (family %d, N %d, bits %d)", family, N, bits); return nullptr; }
+  const uint8_t *dIn = static_cast<const uint8_t *>(dInV);
+  if (!dIn || (reinterpret_cast<uintptr_t>(dIn) & 15)) { set_err("device input must be 16-byte aligned"); return nullptr; }
+  if (inLength < 16 + 4 * (size_t)N + 512) { set_err("input shorter than the fixed header"); return nullptr; }
+  uint8_t hdr[16];
+  CU_TRY(cudaMemcpy(hdr, dIn, 16, cudaMemcpyDeviceToHost), return nullptr);
+  Header h{rd64(hdr), rd64(hdr + 8)};
+  if (inLength < h.compLen) { set_err("inLength %zu < compressed length %llu", inLength, (unsigned long long)h.compLen); return nullptr; }
+  if (h.n < (uint64_t)N || h.compLen < 16 + 4 * (uint64_t)N + 512) { set_err("malformed header"); return nullptr; }
+
+  std::unique_ptr<hsr_stream, void (*)(hsr_stream *)> s(new hsr_stream, stream_release);
+  s->family = family; s->N = N; s->bits = bits; s->n = h.n; s->compLen = h.compLen;
+  CU_TRY(cudaGetDevice(&s->device), return nullptr);
+  s->dIn = const_cast<uint8_t *>(dIn);
+  s->ownsIn = false;
+  s->inBase = 0;
+  s->inBytes = h.compLen;
+  s->outOffset = 0;
+  s->outBytes = h.n;
+
+  if (family == HSR_RAW) {
+    if (h.compLen > kMaxUnitIn) { set_err("raw streams above 4 GiB compressed are not supported"); return nullptr; }
+    s->blocks.push_back(raw_unit(N, h));
+  } else if (family == HSR_MT) {
+    unsigned long long *dRes = nullptr;
+    CU_TRY(cudaMalloc(&dRes, 16), return nullptr);
+    uint64_t cap = std::max<uint64_t>(1024, h.n / 32768 + 64);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int attempt = 0; attempt < 2; attempt++) {
+      hsr_block_t *dB = nullptr;
+      CU_TRY(cudaMalloc(&dB, cap * sizeof(hsr_block_t)), { cudaFree(dRes); return nullptr; });
+      cudaEventRecord(e0);
+      mt_walk_kernel<<<1, 32>>>(dIn, h.compLen, (uint32_t)N, dB, cap, dRes);
+      cudaEventRecord(e1);
+      unsigned long long res[2] = {0, 0};
+      CU_TRY(cudaMemcpy(res, dRes, 16, cudaMemcpyDeviceToHost), { cudaFree(dB); cudaFree(dRes); return nullptr; });
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      s->indexMs += ms;
+      if (res[1]) { set_err("malformed mt_ chain (device walk error %llu)", res[1]); cudaFree(dB); cudaFree(dRes); return nullptr; }
+      if (res[0] <= cap) {
+        s->blocks.resize((size_t)res[0]);
+        CU_TRY(cudaMemcpy(s->blocks.data(), dB, s->blocks.size() * sizeof(hsr_block_t), cudaMemcpyDeviceToHost), { cudaFree(dB); cudaFree(dRes); return nullptr; });
+        cudaFree(dB);
+        break;
+      }
+      cudaFree(dB);
+      cap = res[0];
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(dRes);
+  }
+  if (!stream_finish(s.get())) return nullptr;
+  return s.release();
+}
+
+extern "C" uint64_t hsr_stream_decoded_length(const hsr_stream_t *s) { return s ? s->n : 0; }
+extern "C" uint64_t hsr_stream_shard_out_offset(const hsr_stream_t *s) { return s ? s->outOffset : 0; }
+extern "C" uint64_t hsr_stream_shard_out_bytes(const hsr_stream_t *s) { return s ? s->outBytes : 0; }
+extern "C" uint64_t hsr_stream_shard_in_bytes(const hsr_stream_t *s) { return s ? s->inBytes : 0; }
+extern "C" uint64_t hsr_stream_units(const hsr_stream_t *s) { return s ? (s->family == HSR_BLOCK ? 1 : s->blocks.size()) : 0; }
+extern "C" double hsr_stream_index_ms(const hsr_stream_t *s) { return s ? s->indexMs : 0.0; }
+
+extern "C" int hsr_stream_copy_index(const hsr_stream_t *s, hsr_block_t *blocks, size_t maxBlocks)
+{
+  if (!s || !blocks) return -1;
+  const size_t k = std::min(maxBlocks, s->blocks.size());
+  memcpy(blocks, s->blocks.data(), k * sizeof(hsr_block_t));
+  return (int)k;
+}
+
+extern "C" int hsr_stream_decode_async(hsr_stream_t *s, void *dOutV, size_t outCapacity, unsigned flags, void *cudaStream)
+{
+  if (!s || !dOutV) { set_err("null stream or output"); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(cudaStream);
+  uint8_t *dOut = static_cast<uint8_t *>(dOutV);
+  const bool local = (flags & HSR_OUT_SHARD_LOCAL) != 0;
+  const uint64_t need = local ? s->outBytes : s->n;
+  if (outCapacity < need) { set_err("outCapacity %zu < %llu", outCapacity, (unsigned long long)need); return -1; }
+  const uint64_t outBase = local ? s->outOffset : 0;
+  if (s->family == HSR_BLOCK)
+    return launch_block_stream(s->N, s->bits, s->dIn, s->compLen, dOut, s->n, s->dCounter, st);
+  return launch_units(s->N, s->bits, s->dIn, s->inBase, dOut, outBase, s->dBlocks, (uint32_t)s->blocks.size(), s->dCounter, st);
+}
+
+extern "C" unsigned hsr_stream_status(hsr_stream_t *s)
+{
+  if (!s) return ~0u;
+  uint32_t v[2] = {0, 0};
+  if (cudaMemcpy(v, s->dCounter, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { (void)cudaGetLastError(); return ~0u; }
+  const uint32_t zero = 0;
+  cudaMemcpy(s->dCounter + 1, &zero, 4, cudaMemcpyHostToDevice);
+  return v[1];
+}
+
+// ------------------------------------------------------------------------------------------------ host-pointer decode
+
+// Per-device scratch reused across hsr_decode calls: device buffers grow on demand and are kept, like the
+// reference harness keeps its three buffers for the whole run (src/main.cpp:125-127).
+struct DeviceCtx {
+  std::mutex mu;
+  int device = -1;
+  cudaStream_t sIn = nullptr, sRun = nullptr, sOut = nullptr;
+  uint8_t *dIn = nullptr; size_t inCap = 0;
+  uint8_t *dOut = nullptr; size_t outCap = 0;
+  hsr_block_t *dBlocks = nullptr; size_t blocksCap = 0;
+  uint32_t *dCounters = nullptr; size_t countersCap = 0; // 4 u32 per chunk: counter, status, pad, pad
+  std::vector<cudaEvent_t> evIn, evRun;
+};
+
+static DeviceCtx *get_ctx(int device)
+{
+  static std::mutex mu;
+  static std::vector<std::unique_ptr<DeviceCtx>> ctxs;
+  std::lock_guard<std::mutex> lock(mu);
+  for (auto &c : ctxs)
+    if (c->device == device) return c.get();
+  std::unique_ptr<DeviceCtx> c(new DeviceCtx);
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->sIn, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->sRun, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->sOut, cudaStreamNonBlocking) != cudaSuccess) {
+    set_err("cannot create CUDA streams: %s", cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  ctxs.push_back(std::move(c));
+  return ctxs.back().get();
+}
+
+template <class T>
+static bool grow(T *&p, size_t &cap, size_t need)
+{
+  if (need <= cap) return true;
+  if (p) cudaFree(p);
+  p = nullptr; cap = 0;
+  const size_t want = need + need / 8 + 256;
+  CU_TRY(cudaMalloc(&p, want * sizeof(T)), return false);
+  cap = want;
+  return true;
+}
+
+static bool ensure_events(DeviceCtx *c, size_t nChunks)
+{
+  while (c->evIn.size() < nChunks) {
+    cudaEvent_t a, b;
+    CU_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming), return false);
+    CU_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming), return false);
+    c->evIn.push_back(a); c->evRun.push_back(b);
+  }
+  return true;
+}
+
+// Decodes units [first, last) of an mt_ stream (or the single raw unit) held in host memory on `device`:
+// chunked H2D -> decode -> D2H with the three stages overlapped on three streams.
+static bool decode_units_from_host(int device, int N, int bits, const uint8_t *in, uint8_t *out, const hsr_block_t *units,
+                                   size_t first, size_t last)
+{
+  if (first >= last) return true;
+  CU_TRY(cudaSetDevice(device), return false);
+  DeviceCtx *c = get_ctx(device);
+  if (!c) return false;
+  std::lock_guard<std::mutex> lock(c->mu);
+
+  const uint64_t inLo = units[first].inOffset & ~15ull, inHi = units[last - 1].inEnd;
+  const uint64_t outLo = units[first].outOffset, outHi = units[last - 1].outOffset + units[last - 1].count;
+  const size_t count = last - first;
+
+  // chunk boundaries: contiguous unit ranges of about chunkBytes of compressed + decoded traffic
+  const long optMb = g_optChunkMb;
+  const uint64_t chunkBytes = (optMb > 0 ? (uint64_t)optMb : 32ull) << 20;
+  std::vector<size_t> cuts{first};
+  uint64_t acc = 0;
+  for (size_t k = first; k < last; k++) {
+    acc += (units[k].inEnd - units[k].inOffset) + units[k].count;
+    if (acc >= chunkBytes && k + 1 < last) { cuts.push_back(k + 1); acc = 0; }
+  }
+  cuts.push_back(last);
+  const size_t nChunks = cuts.size() - 1;
+
+  if (!grow(c->dIn, c->inCap, (size_t)(inHi - inLo) + 16)) return false;
+  if (!grow(c->dOut, c->outCap, (size_t)(outHi - outLo) + 16)) return false;
+  if (!grow(c->dBlocks, c->blocksCap, count)) return false;
+  if (!grow(c->dCounters, c->countersCap, nChunks * 4)) return false;
+  if (!ensure_events(c, nChunks)) return false;
+
+  CU_TRY(cudaMemcpyAsync(c->dBlocks, units + first, count * sizeof(hsr_block_t), cudaMemcpyHostToDevice, c->sRun), return false);
+  CU_TRY(cudaMemsetAsync(c->dCounters, 0, nChunks * 16, c->sRun), return false);
+
+  for (size_t ch = 0; ch < nChunks; ch++) {
+    const size_t a = cuts[ch], b = cuts[ch + 1];
+    const uint64_t cLo = ch == 0 ? inLo : units[a].inOffset & ~15ull; // re-sending < 16 bytes keeps copies aligned
+    const uint64_t cHi = units[b - 1].inEnd;
+    CU_TRY(cudaMemcpyAsync(c->dIn + (cLo - inLo), in + cLo, (size_t)(cHi - cLo), cudaMemcpyHostToDevice, c->sIn), return false);
+    CU_TRY(cudaEventRecord(c->evIn[ch], c->sIn), return false);
+    CU_TRY(cudaStreamWaitEvent(c->sRun, c->evIn[ch], 0), return false);
+    if (launch_units(N, bits, c->dIn, inLo, c->dOut, outLo, c->dBlocks + (a - first), (uint32_t)(b - a), c->dCounters + 4 * ch, c->sRun) < 0)
+      return false;
+    CU_TRY(cudaEventRecord(c->evRun[ch], c->sRun), return false);
+    CU_TRY(cudaStreamWaitEvent(c->sOut, c->evRun[ch], 0), return false);
+    const uint64_t oLo = units[a].outOffset, oHi = units[b - 1].outOffset + units[b - 1].count;
+    CU_TRY(cudaMemcpyAsync(out + oLo, c->dOut + (oLo - outLo), (size_t)(oHi - oLo), cudaMemcpyDeviceToHost, c->sOut), return false);
+  }
+  std::vector<uint32_t> status(nChunks * 4);
+  CU_TRY(cudaMemcpyAsync(status.data(), c->dCounters, nChunks * 16, cudaMemcpyDeviceToHost, c->sOut), return false);
+  CU_TRY(cudaStreamSynchronize(c->sOut), return false);
+  CU_TRY(cudaStreamSynchronize(c->sIn), return false);
+  CU_TRY(cudaStreamSynchronize(c->sRun), return false);
+  uint32_t bad = 0;
+  for (size_t ch = 0; ch < nChunks; ch++) bad |= status[4 * ch + 1];
+  if (bad) { set_err("malformed stream (device status 0x%x)", bad); return false; }
+  return true;
+}
+
+static bool decode_block_from_host(int device, int N, int bits, const uint8_t *in, const Header &h, uint8_t *out)
+{
+  CU_TRY(cudaSetDevice(device), return false);
+  DeviceCtx *c = get_ctx(device);
+  if (!c) return false;
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (!grow(c->dIn, c->inCap, (size_t)h.compLen + 16)) return false;
+  if (!grow(c->dOut, c->outCap, (size_t)h.n + 16)) return false;
+  if (!grow(c->dCounters, c->countersCap, 4)) return false;
+  CU_TRY(cudaMemsetAsync(c->dCounters, 0, 16, c->sRun), return false);
+  CU_TRY(cudaMemcpyAsync(c->dIn, in, (size_t)h.compLen, cudaMemcpyHostToDevice, c->sRun), return false);
+  if (launch_block_stream(N, bits, c->dIn, h.compLen, c->dOut, h.n, c->dCounters, c->sRun) < 0) return false;
+  CU_TRY(cudaMemcpyAsync(out, c->dOut, (size_t)h.n, cudaMemcpyDeviceToHost, c->sRun), return false);
+  uint32_t status[4] = {0, 0, 0, 0};
+  CU_TRY(cudaMemcpyAsync(status, c->dCounters, 16, cudaMemcpyDeviceToHost, c->sRun), return false);
+  CU_TRY(cudaStreamSynchronize(c->sRun), return false);
+  if (status[1]) { set_err("malformed stream (device status 0x%x)", status[1]); return false; }
+  return true;
+}
+
+extern "C" size_t hsr_decode(int family, int N, int bits, const uint8_t *in, size_t inLength, uint8_t *out, size_t outCapacity)
+{
+  g_err.clear();
+  if (!valid_codec(family, N, bits)) { set_err("unsupported codec (family %d, N %d, bits %d)", family, N, bits); return 0; }
+  Header h;
+  if (!read_header(N, in, inLength, outCapacity, &h)) return 0;
+  if (!out) { set_err("null output"); return 0; }
+  if (h.compLen < 16 + 4 * (uint64_t)N + 512) { set_err("compressed length field too small"); return 0; }
+  int device = 0;
+  CU_TRY(cudaGetDevice(&device), return 0);
+
+  if (family == HSR_BLOCK)
+    return decode_block_from_host(device, N, bits, in, h, out) ? (size_t)h.n : 0;
+  if (family == HSR_RAW) {
+    if (h.compLen > kMaxUnitIn) { set_err("raw streams above 4 GiB compressed are not supported"); return 0; }
+    const hsr_block_t u = raw_unit(N, h);
+    return decode_units_from_host(device, N, bits, in, out, &u, 0, 1) ? (size_t)h.n : 0;
+  }
+  const long cnt = hsr_mt_index(N, in, (size_t)h.compLen, nullptr, 0);
+  if (cnt < 0) return 0;
+  std::vector<hsr_block_t> units((size_t)cnt);
+  if (hsr_mt_index(N, in, (size_t)h.compLen, units.data(), units.size()) != cnt) return 0;
+  return decode_units_from_host(device, N, bits, in, out, units.data(), 0, units.size()) ? (size_t)h.n : 0;
+}
+
+extern "C" size_t hsr_decode_mt_multi(int N, int bits, const uint8_t *in, size_t inLength, uint8_t *out, size_t outCapacity,
+                                      const int *devices, int deviceCount)
+{
+  g_err.clear();
+  if (!valid_codec(HSR_MT, N, bits)) { set_err("unsupported codec (N %d, bits %d)", N, bits); return 0; }
+  if (deviceCount < 1) { set_err("deviceCount must be >= 1"); return 0; }
+  Header h;
+  if (!read_header(N, in, inLength, outCapacity, &h)) return 0;
+  if (!out) { set_err("null output"); return 0; }
+  const long cnt = hsr_mt_index(N, in, (size_t)h.compLen, nullptr, 0);
+  if (cnt < 0) return 0;
+  std::vector<hsr_block_t> units((size_t)cnt);
+  if (hsr_mt_index(N, in, (size_t)h.compLen, units.data(), units.size()) != cnt) return 0;
+  std::vector<size_t> first((size_t)deviceCount + 1);
+  hsr_mt_partition(units.data(), units.size(), deviceCount, first.data());
+
+  int prev = 0;
+  cudaGetDevice(&prev);
+  std::vector<std::thread> workers;
+  std::vector<std::string> errors((size_t)deviceCount);
+  std::vector<char> ok((size_t)deviceCount, 0);
+  for (int d = 0; d < deviceCount; d++) {
+    workers.emplace_back([&, d]() {
+      const int dev = devices ? devices[d] : d;
+      ok[d] = decode_units_from_host(dev, N, bits, in, out, units.data(), first[d], first[d + 1]);
+      if (!ok[d]) errors[d] = g_err;
+    });
+  }
+  for (auto &w : workers) w.join();
+  cudaSetDevice(prev);
+  for (int d = 0; d < deviceCount; d++)
+    if (!ok[d]) { set_err("device shard %d: %s", d, errors[d].c_str()); return 0; }
+  return (size_t)h.n;
+}

@@ -1,0 +1,222 @@
+// hsr_kernels.cuh — kernel bodies shared by the per-(bits, N, table) instantiation units.
+#pragma once
+
+#include "hsr_device.cuh"
+
+namespace hsr {
+
+// Everything a decode launch needs. Offsets inside hsr_block_t are absolute stream / output offsets; `in` and
+// `out` point at stream offset inBase and decoded offset outBase (shards hold only their slice).
+struct DecodeParams {
+  const uint8_t *in;
+  uint64_t inBase;
+  uint8_t *out;
+  uint64_t outBase;
+  const hsr_block_t *blocks;
+  uint32_t numBlocks;
+  uint32_t *counter; // [0] work counter, [1] status bits
+};
+
+struct BlockStreamParams { // block_ framing: one sequential recurrence
+  const uint8_t *in;
+  uint64_t inLength;
+  uint8_t *out;
+  uint64_t n;
+  uint32_t *counter; // [1] status bits
+};
+
+__device__ __forceinline__ void raise(uint32_t *counter, uint32_t bits, uint32_t lane)
+{
+  if (lane == 0)
+    atomicOr(counter + 1, bits);
+}
+
+// ---------------------------------------------------------------------------------------------- mt_ / raw
+
+// Persistent warps pull units (mt_ blocks, fills, or one raw stream) from a global counter. Each warp owns a
+// private slice of shared memory: tables for its current block + its word ring.
+template <int BITS, int N, int TK, int WARPS>
+__device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
+{
+  using L = WarpLayout<BITS, N, TK>;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t lane = lane_id();
+  const uint32_t warp = threadIdx.x >> 5;
+  uint8_t *sw = smem + warp * L::kBytes;
+  const uint32_t ltMask = lanemask_lt();
+  const uint32_t lanePos = idx2idx_lane(lane);
+
+  Decoder<BITS, N, TK> dec;
+  dec.init(sw);
+
+  for (;;) {
+    uint32_t b = 0;
+    if (lane == 0)
+      b = atomicAdd(p.counter, 1u);
+    b = __shfl_sync(kFull, b, 0);
+    if (b >= p.numBlocks)
+      break;
+
+    const hsr_block_t *blk = p.blocks + b;
+    const uint64_t inOffset = __ldg(&blk->inOffset);
+    const uint64_t inEnd = __ldg(&blk->inEnd);
+    const uint64_t outOffset = __ldg(&blk->outOffset);
+    const uint64_t count = __ldg(&blk->count);
+    const uint32_t kind = __ldg(&blk->kind);
+    const uint32_t tailCount = __ldg(&blk->tail);
+    uint8_t *out = p.out + (outOffset - p.outBase);
+
+    if (kind == 1u) {
+      warp_fill(out, __ldg(&blk->symbol), count, lane);
+      continue;
+    }
+
+    const uint8_t *base = p.in + (inOffset - p.inBase);
+    const uint8_t *end = p.in + (inEnd - p.inBase);
+    const uint8_t *statesPtr = kind == 0u ? base : base + 512;     // mt_: states then counts; raw: counts then states
+    const uint8_t *countsPtr = kind == 0u ? base + 4 * N : base;
+    const uint8_t *words = base + 4 * N + 512;
+
+    if (!build_tables<BITS, N, TK>(sw, countsPtr, lane)) {
+      raise(p.counter, HSR_ERR_HIST, lane);
+      continue;
+    }
+    if constexpr (TK == TK_PACKED)
+      dec.degenerate = table_is_degenerate<BITS, N, TK>(sw);
+
+    uint32_t x0 = ldg_u32_a2(statesPtr + 4 * lane);
+    uint32_t x1 = 0;
+    if constexpr (N == 64)
+      x1 = ldg_u32_a2(statesPtr + 4 * (lane + 32));
+
+    WordRing<L> ring;
+    ring.start(smem_u32(sw + L::kOffRing), words, end, lane);
+
+    const uint64_t rows = (count - tailCount) / N;
+    uint8_t *outLane = out + lanePos;
+    dec.rows(x0, x1, ring, outLane, rows, lane, ltMask);
+    if (tailCount)
+      dec.tail(x0, x1, ring, outLane + rows * N, lanePos, tailCount, lane, ltMask);
+    ring.drain();
+    if (ring.cur > ring.glimit)
+      raise(p.counter, HSR_ERR_OVERRUN, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- block_
+
+// block_ framing (src/block_rANS32x32_16w_decode.cpp:18-142): the N states are read once and carried through
+// every block; each block header sits in-band at the word cursor, so block k+1 cannot be located before block k
+// has been decoded. One warp walks the whole stream, rebuilding its tables between sections.
+template <int BITS, int N, int TK>
+__device__ __forceinline__ void block_kernel_body(const BlockStreamParams &p)
+{
+  using L = WarpLayout<BITS, N, TK>;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t lane = lane_id();
+  uint8_t *sw = smem;
+  const uint32_t ltMask = lanemask_lt();
+  const uint32_t lanePos = idx2idx_lane(lane);
+
+  Decoder<BITS, N, TK> dec;
+  dec.init(sw);
+
+  const uint8_t *in = p.in;
+  const uint8_t *streamEnd = p.in + p.inLength;
+  uint64_t pos = 16;
+  uint32_t x0 = ldg_u32_a2(in + pos + 4 * lane);
+  uint32_t x1 = 0;
+  if constexpr (N == 64)
+    x1 = ldg_u32_a2(in + pos + 4 * (lane + 32));
+  pos += 4 * N;
+
+  const uint64_t n = p.n;
+  const uint64_t outLengthInStates = n - N + 1;
+  uint64_t i = 0;
+  bool haveHist = false;
+  WordRing<L> ring;
+  const uint32_t sRing = smem_u32(sw + L::kOffRing);
+
+  do {
+    if (pos + 8 > p.inLength) {
+      raise(p.counter, HSR_ERR_OVERRUN, lane);
+      return;
+    }
+    const uint64_t v = ldg_u64_a2(in + pos);
+    pos += 8;
+    if (v >> 63) { // single-symbol run (:58-66)
+      const uint32_t symbol = (uint32_t)(v >> 54) & 0xffu;
+      const uint64_t size = v & ((1ull << 54) - 1);
+      if (size > n - i) {
+        raise(p.counter, HSR_ERR_BOUNDS, lane);
+        return;
+      }
+      warp_fill(p.out + i, symbol, size, lane);
+      i += size;
+    } else {
+      if (pos + 512 > p.inLength) {
+        raise(p.counter, HSR_ERR_OVERRUN, lane);
+        return;
+      }
+      if (!build_tables<BITS, N, TK>(sw, in + pos, lane)) { // :69-76
+        raise(p.counter, HSR_ERR_HIST, lane);
+        return;
+      }
+      if constexpr (TK == TK_PACKED)
+        dec.degenerate = table_is_degenerate<BITS, N, TK>(sw);
+      haveHist = true;
+      pos += 512;
+
+      uint64_t blockEnd = i + v; // :78-83
+      if (blockEnd > outLengthInStates)
+        blockEnd = outLengthInStates;
+      else if (blockEnd & (N - 1)) {
+        raise(p.counter, HSR_ERR_ALIGN, lane);
+        return;
+      }
+      const uint64_t rows = blockEnd > i ? (blockEnd - i + N - 1) / N : 0;
+      ring.start(sRing, in + pos, streamEnd, lane);
+      dec.rows(x0, x1, ring, p.out + i + lanePos, rows, lane, ltMask);
+      ring.drain();
+      if (ring.cur > ring.glimit) {
+        raise(p.counter, HSR_ERR_OVERRUN, lane);
+        return;
+      }
+      pos = (uint64_t)(ring.gbase - in) + ring.cur;
+      i += rows * N;
+    }
+    if (i > outLengthInStates) { // :88-94
+      if (i >= n)
+        return;
+      break;
+    }
+  } while (i < outLengthInStates);
+
+  if (i < n) { // :98-139
+    if (!haveHist) {
+      raise(p.counter, HSR_ERR_HIST, lane);
+      return;
+    }
+    ring.start(sRing, in + pos, streamEnd, lane);
+    dec.tail(x0, x1, ring, p.out + i + lanePos, lanePos, (uint32_t)(n - i), lane, ltMask);
+    ring.drain();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- launch table
+
+typedef void (*units_kernel_t)(DecodeParams);
+typedef void (*block_kernel_t)(BlockStreamParams);
+
+struct KernelEntry {
+  const void *unitsW4; // 4 warps per CTA (mt_)
+  const void *unitsW1; // 1 warp per CTA (raw: one stream)
+  const void *block;   // block_ framing, 1 warp
+  int warpBytes;       // shared memory per warp
+};
+
+// defined in hsr_kernels_n32.cu / hsr_kernels_n64.cu; index [bits - 10][table - 1]
+extern const KernelEntry kKernels32[6][2];
+extern const KernelEntry kKernels64[6][2];
+
+} // namespace hsr

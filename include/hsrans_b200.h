@@ -1,0 +1,164 @@
+/*
+ * hsrans_b200.h — C-ABI of the B200-native (sm_100a) decoder for hypersonic-rANS's interleaved
+ * 32-bit-state / 16-bit-word streams: rANS32x32_16w, rANS32x64_16w, block_rANS32x{32,64}_16w and
+ * mt_rANS32x{32,64}_16w, probability bits 10..15, plus the histogram count/normalise step.
+ *
+ * Plain pointers and sizes only; no torch, no C++ types. Every entry point names the reference interface it
+ * replaces (file:line relative to the reference repository). The shared object is
+ * hypersonic-rans_b200/libhsrans_b200.so; C++ callers can use hypersonic-rans_b200/cpp/hsrans_b200_codecs.hpp,
+ * which wraps these calls in functions that carry the reference's exact per-bits names and `decodeFunc` type.
+ *
+ * Conventions copied from the reference (src/rANS32x32_16w.cpp:164-191): decoders return the decoded byte
+ * count on success and 0 on ANY error (short input, capacity too small, histogram not summing to 2^bits,
+ * misaligned block end, CUDA failure, no GPU). There is no CPU fallback: without a usable CUDA device every
+ * compute entry point returns 0 / a negative status and hsr_last_error() says why.
+ */
+#ifndef HSRANS_B200_H
+#define HSRANS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSR_VERSION 100
+
+/* Stream framings (SURVEY.md §8a "Stream formats"). */
+typedef enum hsr_family {
+  HSR_RAW = 0,   /* rANS32xN_16w        — one histogram, one recurrence   (src/rANS32x32_16w.cpp:130-158)            */
+  HSR_BLOCK = 1, /* block_rANS32xN_16w  — in-band histograms, carried states (src/block_rANS32x32_16w_encode.cpp:262-285) */
+  HSR_MT = 2     /* mt_rANS32xN_16w     — independent blocks with state snapshots (src/mt_rANS32x64_16w_encode.cpp:266-298) */
+} hsr_family_t;
+
+/* ------------------------------------------------------------------------------------------------ general */
+
+int hsr_version(void);
+/* Number of usable CUDA devices (0 if none / driver missing). */
+int hsr_device_count(void);
+/* Thread-local description of the last failure in this thread ("" if none). */
+const char *hsr_last_error(void);
+/* Tuning knobs, for benchmarking variants without rebuilding. Unknown keys return -1.
+ *   "table"      0 = auto (packed slot table for bits <= 12, bitmap-rank table above), 1 = bitmap-rank, 2 = packed
+ *   "warps"      warps per CTA for the mt_ kernel (1..16, 0 = auto)
+ *   "chunk_mb"   host pipeline chunk size in MiB for hsr_decode on mt_ streams (0 = auto)                      */
+int hsr_set_option(const char *key, long value);
+long hsr_get_option(const char *key);
+
+/* Worst-case compressed size for n input bytes; identical for all three framings.
+ * Replaces rANS32x32_16w_capacity (src/rANS32x32_16w.cpp:10-13), block_rANS32x32_16w_capacity
+ * (src/block_rANS32x32_16w_encode.cpp:47-54), mt_rANS32x64_16w_capacity (src/mt_rANS32x64_16w_encode.cpp:50-57). */
+size_t hsr_capacity(int stateCount, size_t inputSize);
+
+/* Page-locked host buffers for the harness (the reference harness allocates 64-byte aligned buffers,
+ * src/main.cpp:649-650). hsr_decode accepts any host pointer; pinned ones avoid a staging copy. */
+void *hsr_host_alloc(size_t bytes);
+void hsr_host_free(void *p);
+
+/* ------------------------------------------------------------------------------------------------ drop-in decode */
+
+/* Host-pointer decode: H2D, index (mt_), kernels, D2H, synchronise. Replaces every function of type
+ *   size_t f(const uint8_t *pInData, const size_t inLength, uint8_t *pOutData, const size_t outCapacity)
+ * i.e. codec_info_t::decodeFunc (src/main.cpp:149): rANS32x32_16w_decode_scalar_<b> (src/rANS32x32_16w.cpp:161),
+ * rANS32x64_16w_decode_scalar_<b> (src/rANS32x64_16w.cpp:168) and all their AVX variants,
+ * block_rANS32xNN_16w_decode_<b> (src/block_rANS32x32_16w_decode.cpp:165-193),
+ * mt_rANS32xNN_16w_decode_<b> / _decode_mt_<b> (src/mt_rANS32x64_16w_decode.cpp:301-361).
+ * Uses the current CUDA device (hsr_set_device). Re-entrant across threads; one internal context per device. */
+size_t hsr_decode(int family, int stateCount, int bits, const uint8_t *pInData, size_t inLength, uint8_t *pOutData,
+                  size_t outCapacity);
+/* Same, mt_ only, sharding the block chain over `deviceCount` GPUs of this box from ONE process by contiguous
+ * block ranges balanced on compressed bytes (the GPU analogue of the thread pool in
+ * src/mt_rANS32x64_16w_decode.cpp:137-265). devices == NULL means 0..deviceCount-1. */
+size_t hsr_decode_mt_multi(int stateCount, int bits, const uint8_t *pInData, size_t inLength, uint8_t *pOutData,
+                           size_t outCapacity, const int *devices, int deviceCount);
+
+int hsr_set_device(int device);
+
+/* ------------------------------------------------------------------------------------------------ mt_ index (host) */
+
+/* One unit of work for the kernels. For mt_ it is one block of the chain; single-symbol runs are split into
+ * fills of bounded size. */
+typedef struct hsr_block {
+  uint64_t inOffset;  /* coded: byte offset of the block's u32 states[N] (mt_) or of the u16 counts (raw) */
+  uint64_t inEnd;     /* coded: byte offset one past the block's last word */
+  uint64_t outOffset; /* first decoded byte of this unit */
+  uint64_t count;     /* decoded bytes in this unit (coded: rows*N, plus `tail` extra lanes on the last one) */
+  uint32_t kind;      /* 0 coded mt_ layout, 1 fill, 2 coded raw layout */
+  uint32_t symbol;    /* fill value for kind 1 */
+  uint32_t tail;      /* 0, or the number of leftover symbols (< N) decoded after the last full row */
+  uint32_t reserved;
+} hsr_block_t;
+
+/* Walks the mt_ header chain on the host (src/mt_rANS32x64_16w_decode.cpp:40-66,94 — the serial walk the
+ * reference does on the calling thread). Writes up to maxBlocks records; returns the number of units, or -1 on a
+ * malformed chain. Call with blocks == NULL to count. */
+long hsr_mt_index(int stateCount, const uint8_t *pInData, size_t inLength, hsr_block_t *blocks, size_t maxBlocks);
+
+/* Contiguous partition of `count` units over `parts` shards, balanced on compressed bytes + decoded bytes.
+ * firstUnit must hold parts+1 entries; shard p owns units [firstUnit[p], firstUnit[p+1]). */
+int hsr_mt_partition(const hsr_block_t *blocks, size_t count, int parts, size_t *firstUnit);
+
+/* ------------------------------------------------------------------------------------------------ device-resident API */
+
+/* A stream prepared for repeated device-side decoding: the compressed bytes in HBM (byte-exact stream format,
+ * 16-byte aligned base) plus the block index. This is what `value` in bench.py times. */
+typedef struct hsr_stream hsr_stream_t;
+
+/* Upload from host memory to the current device; mt_: also builds and uploads the index. For mt_ a shard can be
+ * selected with (shard, shards): only that contiguous block range is uploaded and decoded (one process per GPU).
+ * Returns NULL on error. */
+hsr_stream_t *hsr_stream_upload(int family, int stateCount, int bits, const uint8_t *pInData, size_t inLength, int shard,
+                                int shards);
+/* Wrap compressed bytes that already live in device memory (16-byte aligned, readable up to inLength).
+ * mt_: the header chain is walked by a device kernel (serial; see hsr_stream_index_ms). */
+hsr_stream_t *hsr_stream_from_device(int family, int stateCount, int bits, const void *dIn, size_t inLength);
+void hsr_stream_free(hsr_stream_t *s);
+
+uint64_t hsr_stream_decoded_length(const hsr_stream_t *s); /* header n (whole stream) */
+uint64_t hsr_stream_shard_out_offset(const hsr_stream_t *s); /* first decoded byte owned by this shard */
+uint64_t hsr_stream_shard_out_bytes(const hsr_stream_t *s);  /* decoded bytes owned by this shard */
+uint64_t hsr_stream_shard_in_bytes(const hsr_stream_t *s);   /* compressed bytes resident for this shard */
+uint64_t hsr_stream_units(const hsr_stream_t *s);
+double hsr_stream_index_ms(const hsr_stream_t *s);           /* time spent building the block index */
+int hsr_stream_copy_index(const hsr_stream_t *s, hsr_block_t *blocks, size_t maxBlocks);
+
+/* Launch the decode of the prepared stream into device memory on `cudaStream` (a cudaStream_t, may be NULL).
+ * dOut is the base of the WHOLE decoded buffer (shards write at their own offsets) and must hold
+ * hsr_stream_decoded_length bytes — or, with HSR_OUT_SHARD_LOCAL, only this shard's bytes.
+ * Asynchronous; returns the number of kernels launched (>0) or a negative status. */
+#define HSR_OUT_SHARD_LOCAL 1u
+int hsr_stream_decode_async(hsr_stream_t *s, void *dOut, size_t outCapacity, unsigned flags, void *cudaStream);
+/* After synchronising: 0 if the last decode saw a well-formed stream, else a bit set of HSR_ERR_*. */
+#define HSR_ERR_HIST 1u     /* a histogram does not sum to 2^bits (src/hist.cpp:308-324) */
+#define HSR_ERR_OVERRUN 2u  /* the word cursor ran past the block / stream end */
+#define HSR_ERR_ALIGN 4u    /* block end not a multiple of the state count (src/block_rANS32x32_16w_decode.cpp:82-83) */
+#define HSR_ERR_BOUNDS 8u   /* a block would write past the decoded length */
+unsigned hsr_stream_status(hsr_stream_t *s);
+
+/* ------------------------------------------------------------------------------------------------ histogram */
+
+/* Replaces make_hist (src/hist.cpp:217-222) = observe_hist (:8-14) + normalize_hist (:16-215), bit-exact.
+ * Host-pointer form: copies the data to the device, counts with a shared-memory-atomic kernel, normalises on
+ * the device with the reference's exact float and heap-sort sequence, returns the 256 counts and cumuls. */
+int hsr_make_hist(const uint8_t *pData, size_t size, int bits, uint16_t symbolCount[256], uint16_t cumul[256]);
+/* Device-pointer forms. dHist: 256 x u32 byte counts. dSymbolCount/dCumul: 256 x u16 each. */
+int hsr_observe_hist_device(const void *dData, size_t size, uint32_t *dHist, void *cudaStream);
+int hsr_normalize_hist_device(const uint32_t *dHist, size_t dataBytes, int bits, uint16_t *dSymbolCount,
+                              uint16_t *dCumul, void *cudaStream);
+/* Segmented form for block_/mt_ style per-block histograms: segment k covers bytes [k*segmentBytes,
+ * min((k+1)*segmentBytes, size)); writes 256 u16 counts per segment, each summing to 2^bits. */
+int hsr_make_hist_segments_device(const void *dData, size_t size, size_t segmentBytes, int bits,
+                                  uint16_t *dSymbolCounts, void *cudaStream);
+
+/* ------------------------------------------------------------------------------------------------ synthetic inputs */
+
+/* Deterministic Zipf(s) bytes over 256 symbols. segmentBytes == 0: one rank->byte permutation
+ * for the whole buffer ("iid"); otherwise the permutation is re-drawn every segmentBytes ("pw64k" = 65536).
+ * Host-side, multi-threaded; not on the decode path. */
+int hsr_synth_zipf(uint8_t *out, size_t n, double s, uint64_t seed, size_t segmentBytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSRANS_B200_H */
