@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py — decoded GB/s of the B200 rANS decoder on BASELINE.json's headline configuration.
+
+Workload (config 4 of BASELINE.json, the one its metric "per GPU & whole box (1/2/4/8 B200)" is quoted on):
+mt_rANS32x64_16w, 15 probability bits, 1,000,000,000-byte synthetic Zipf(s=1) stream per GPU, `pw64k` shape
+(rank->byte permutation re-drawn every 64 KiB so the reference's mt_ encoder emits ~15 k independent blocks per
+GB). At N > 1 every rank decodes its own contiguous block range of the logical N-GB stream — its own
+1 GB shard, weak scaling, no data-path collective.
+
+A "step" is one pass of the decode path over the whole (per-rank) stream:
+  value  kernel path, compressed stream + block index already resident in HBM (hsr_stream_decode_async), CUDA events
+         on the launching stream around exactly K steps, max over ranks.
+  e2e    the drop-in host-pointer call hsr_decode() with pinned HOST buffers: header walk, H2D, kernels, D2H inside
+         the timed region, every step.
+  roofline       algorithmic bytes (compressed in + decoded out) / mean kernel step duration vs the measured HBM peak.
+  cpu_baseline   the reference's own decoders (oracle/_ref, compiled unmodified) on this box's host cores.
+
+The input streams are produced by the reference's own, unmodified encoder (oracle/_ref) during set-up, as the
+north star requires; that and the CPU baseline are the only places this file executes anything under oracle/.
+The timed GPU path never does.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FAMILY_MT = 2
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=1_000_000_000, help="decoded bytes per GPU")
+    ap.add_argument("--bits", type=int, default=15)
+    ap.add_argument("--states", type=int, default=64)
+    ap.add_argument("--shape", default="pw64k", choices=["pw64k", "iid"])
+    ap.add_argument("--zipf", type=float, default=1.0)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extra", action="store_true", help="also report BASELINE configs 2 and 3 (single-recurrence codecs)")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"mt_rANS32x{a.states}_16w {a.bits}-bit decode, {a.size:,}-byte Zipf(s={a.zipf:g}) {a.shape} stream per GPU "
+            f"(BASELINE config 4)")
+
+
+def make_input(pkg, a, rank):
+    """Synthetic bytes + the reference-encoded mt_ stream for this rank's shard (set-up, untimed)."""
+    import checkers as ck
+    if not ck.have_ref():
+        raise RuntimeError("oracle/_ref/libhsrans_ref.so is missing: the input streams must come from the reference's "
+                           "own encoder (build it in the container with `make -C oracle ref`; it travels with gpurun)")
+    seg = 65536 if a.shape == "pw64k" else 0
+    data = pkg.synth_zipf(a.size, a.zipf, seed=42 + rank, segment_bytes=seg)
+    t0 = time.time()
+    stream = ck.ref_encode(FAMILY_MT, a.states, a.bits, data)
+    return data, stream, time.time() - t0
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons of one GPU with NVML while a timed region runs."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_baseline(a, stream, n, reps=3):
+    """The reference's own mt_ decoders on the host cores: thread pool (all cores) and single thread (AVX2 dispatch)."""
+    import checkers as ck
+    lib = ck.ref()
+    cores = os.cpu_count() or 1
+    threads = lib.hsref_pool_create(0)  # hardware_concurrency() - 1 workers + the calling thread (src/main.cpp:167)
+    padded = np.zeros(stream.size + 128, np.uint8)
+    padded[: stream.size] = stream
+    out = np.empty(n + 64, np.uint8)
+
+    def run(impl):
+        best = None
+        for _ in range(reps + 1):  # first run is the dry run (src/main.cpp:862-866)
+            t0 = time.perf_counter()
+            got = lib.hsref_decode(FAMILY_MT, a.states, a.bits, impl, padded.ctypes.data, stream.size, out.ctypes.data, n)
+            dt = time.perf_counter() - t0
+            if got != n:
+                raise RuntimeError("reference decoder failed on its own stream")
+            best = dt if best is None else min(best, dt)
+        return n / best / 1e9
+
+    pool = run(ck.IMPL_POOL)
+    single = run(ck.IMPL_SCALAR)
+    lib.hsref_pool_destroy()
+    return {"value": round(pool, 4), "unit": "GB/s", "cores": threads + 1, "kind": "reference",
+            "sample": f"whole {n:,}-byte stream, best of {reps} after a dry run, mt_rANS32x{a.states}_16w_decode_mt_{a.bits} "
+                      f"with {threads} pool threads + caller",
+            "single_thread_gbs": round(single, 4), "host_cores": cores, "cpu": lib.hsref_cpu_name().decode(errors="replace").strip()}
+
+
+def run_reference(a, rank, world):
+    """--impl reference: the reference's own CPU implementation, rank 0 only."""
+    if rank != 0:
+        return
+    import __graft_entry__ as entry
+    pkg = entry.load_package()
+    data, stream, enc_s = make_input(pkg, a, 0)
+    n = data.size
+    import checkers as ck
+    lib = ck.ref()
+    threads = lib.hsref_pool_create(0)
+    padded = np.zeros(stream.size + 128, np.uint8)
+    padded[: stream.size] = stream
+    out = np.empty(n + 64, np.uint8)
+
+    def step():
+        got = lib.hsref_decode(FAMILY_MT, a.states, a.bits, ck.IMPL_POOL, padded.ctypes.data, stream.size, out.ctypes.data, n)
+        if got != n:
+            raise RuntimeError("reference decoder failed")
+
+    for _ in range(a.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step()
+    dt = time.perf_counter() - t0
+    assert np.array_equal(out[:n], data)
+    gbs = n * a.steps / dt / 1e9
+    line = {
+        "impl": "reference", "metric": "decoded_GBps", "value": round(gbs, 4), "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": round(dt / a.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "note": "reference CPU thread-pool decoder on rank 0's 1 GB shard"},
+        "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": threads + 1, "kind": "reference",
+                         "sample": f"whole {n:,}-byte stream per step, mt_rANS32x{a.states}_16w_decode_mt_{a.bits}"},
+        "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def single_recurrence_extras(pkg, torch, a):
+    """BASELINE configs 2 and 3: one stream = one warp; latency-bound by construction (SURVEY.md finding 1)."""
+    import checkers as ck
+    res = {}
+    n = 100_000_000
+    data = pkg.synth_zipf(n, 1.0, seed=42, segment_bytes=0)
+    out = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
+    for label, fam, states, bits in (("rANS32x64_16w_12_raw", 0, 64, 12), ("block_rANS32x32_16w_10", 1, 32, 10),
+                                     ("rANS32x32_16w_11_raw", 0, 32, 11)):
+        stream = ck.ref_encode(fam, states, bits, data)
+        ps = pkg.PreparedStream.upload(fam, states, bits, stream)
+        st = torch.cuda.current_stream().cuda_stream
+        ps.decode_async(out.data_ptr(), n, st)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ps.decode_async(out.data_ptr(), n, st)
+        e1.record()
+        torch.cuda.synchronize()
+        ok = ps.status() == 0 and bool(np.array_equal(out[:n].cpu().numpy(), data))
+        ms = e0.elapsed_time(e1)
+        cpu_n, cpu_out = None, None
+        t0 = time.perf_counter()
+        cpu_n, cpu_out = ck.ref_decode(fam, states, bits, stream, n, ck.IMPL_AVX2)
+        cpu_s = time.perf_counter() - t0
+        res[label] = {"gpu_decoded_GBps": round(n / ms / 1e6, 4), "gpu_ms": round(ms, 3), "bit_exact": ok,
+                      "cpu_avx2_1thread_GBps": round(n / cpu_s / 1e9, 4), "streams": 1, "warps": 1}
+        ps.free()
+    return res
+
+
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    pkg = entry.load_package()
+    if pkg.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (" + pkg.last_error() + ")")
+    torch.cuda.set_device(local_rank)
+    pkg.lib().hsr_set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    data, stream, enc_s = make_input(pkg, a, rank)
+    n = data.size
+    comp = stream.size
+
+    # ---------------------------------------------------------------- kernel path: stream + index resident in HBM
+    ps = pkg.PreparedStream.upload(FAMILY_MT, a.states, a.bits, stream)
+    units = ps.units
+    out_dev = torch.empty(n + 256, dtype=torch.uint8, device="cuda")
+    cur = torch.cuda.current_stream().cuda_stream
+    launches_per_step = ps.decode_async(out_dev.data_ptr(), n, cur)
+    torch.cuda.synchronize()
+    if ps.status() != 0 or not np.array_equal(out_dev[:n].cpu().numpy(), data):
+        raise SystemExit(f"rank {rank}: GPU output differs from the original bytes — refusing to report a number")
+    for _ in range(a.warmup):
+        ps.decode_async(out_dev.data_ptr(), n, cur)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    with ClockSampler(local_rank) as clk:
+        ev[0].record()
+        for k in range(a.steps):
+            ps.decode_async(out_dev.data_ptr(), n, cur)
+            ev[k + 1].record()
+        barrier()
+    total_ms = ev[0].elapsed_time(ev[a.steps])
+    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(a.steps)]
+    total_ms = max_over_ranks(total_ms)
+    ms_per_step = total_ms / a.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e9
+    clocks = clk.summary()
+
+    # ---------------------------------------------------------------- end to end through the drop-in host call
+    e2e_steps = a.e2e_steps or min(a.steps, 10)
+    hin, hout = pkg.host_alloc(comp), pkg.host_alloc(n)
+    hin.array[:] = stream
+    lib = pkg.lib()
+
+    def e2e_step():
+        got = lib.hsr_decode(FAMILY_MT, a.states, a.bits, hin.ptr, comp, hout.ptr, n)
+        if got != n:
+            raise SystemExit(f"rank {rank}: hsr_decode failed: {pkg.last_error()}")
+
+    for _ in range(max(1, min(a.warmup, 3))):
+        e2e_step()
+    if not np.array_equal(hout.array, data):
+        raise SystemExit(f"rank {rank}: end-to-end output differs from the original bytes")
+    barrier()
+    with ClockSampler(local_rank) as clk2:
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+    e2e_s = max_over_ranks(e2e_s)
+    e2e_value = world * n * e2e_steps / e2e_s / 1e9
+
+    # ---------------------------------------------------------------- index timings (reported apart, SURVEY §8d "I")
+    index_host_ms = ps.index_ms
+    dev_in = torch.from_numpy(stream).cuda()
+    ds = pkg.PreparedStream.from_device(FAMILY_MT, a.states, a.bits, dev_in.data_ptr(), comp)
+    index_device_ms = ds.index_ms
+    ds.free()
+    del dev_in
+
+    comp_total = sum_over_ranks(float(comp))
+    units_total = sum_over_ranks(float(units))
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+        kernel_ms = float(np.mean(step_ms))
+        achieved = (comp + n) / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "decoded_GBps", "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "codec": f"mt_rANS32x{a.states}_16w", "bits": a.bits, "shape": a.shape,
+                       "decoded_bytes_per_gpu": n, "compressed_bytes_per_gpu": comp, "blocks_per_gpu": int(units),
+                       "blocks_total": int(units_total), "compressed_bytes_total": int(comp_total),
+                       "stream_producer": "reference mt_ encoder (oracle/_ref), unmodified",
+                       "l2_policy": "inputs larger than L2: 1.78 GB touched per step vs 126 MB L2",
+                       "parallelism": f"{world} x contiguous block range, no collective",
+                       "table": "auto (bitmap-rank for bits>=13, packed slot table below)"},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": traffic, "peak_source": peak_src, "kernel": f"units_w4_n{a.states}_b{a.bits}",
+                         "algorithmic_bytes_per_launch": comp + n, "kernel_ms": round(kernel_ms, 4),
+                         "kernel_ms_min": round(float(np.min(step_ms)), 4)},
+            "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": comp, "d2h_bytes_per_step": n,
+                    "steps": e2e_steps, "ms_per_step": round(e2e_s / e2e_steps * 1e3, 3), "api": "hsr_decode (host pointers, pinned)"},
+            "gpu_launches": int(launches_per_step * a.steps),
+            "clocks": clocks, "clocks_e2e": clk2.summary(),
+            "index_ms": {"host_walk": round(index_host_ms, 3), "device_walk": round(index_device_ms, 3)},
+            "setup_s": {"reference_encode": round(enc_s, 2)},
+        }
+        if not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(a, stream, n)
+        if a.extra:
+            line["single_recurrence"] = single_recurrence_extras(pkg, torch, a)
+        print(json.dumps(line), flush=True)
+    ps.free()
+    hin.free(); hout.free()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

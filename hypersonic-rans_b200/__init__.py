@@ -13,3 +13,4 @@ from .capi import (  # noqa: F401
     mt_partition, make_hist, synth_zipf, observe_hist_device, normalize_hist_device, make_hist_segments_device,
 )
 from .codecs import CODECS, Codec, find_codec  # noqa: F401
+from .sharding import ShardPlan, plan_shards, assemble_on  # noqa: F401

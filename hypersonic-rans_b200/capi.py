@@ -35,7 +35,7 @@ SIGNATURES = {
     "hsr_last_error": (C.c_char_p, []),
     "hsr_set_option": (C.c_int, [C.c_char_p, C.c_long]),
     "hsr_get_option": (C.c_long, [C.c_char_p]),
-    "hsr_capacity": (C.c_size_t, [C.c_int, C.c_size_t]),
+    "hsr_capacity": (C.c_size_t, [C.c_int, C.c_int, C.c_size_t]),
     "hsr_host_alloc": (C.c_void_p, [C.c_size_t]),
     "hsr_host_free": (None, [C.c_void_p]),
     "hsr_decode": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
@@ -101,8 +101,8 @@ def get_option(key: str) -> int:
     return lib().hsr_get_option(key.encode())
 
 
-def capacity(state_count: int, n: int) -> int:
-    return lib().hsr_capacity(state_count, n)
+def capacity(family: int, state_count: int, n: int) -> int:
+    return lib().hsr_capacity(family, state_count, n)
 
 
 def _ptr(a: np.ndarray) -> int:

@@ -25,7 +25,7 @@ class Codec:
         return capi.decode(self.family, self.state_count, self.bits, data, out_capacity, out)
 
     def capacity(self, n: int) -> int:
-        return capi.capacity(self.state_count, n)
+        return capi.capacity(self.family, self.state_count, n)
 
 
 def _rows() -> List[Codec]:

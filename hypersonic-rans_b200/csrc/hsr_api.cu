@@ -87,10 +87,18 @@ extern "C" long hsr_get_option(const char *key)
   return -1;
 }
 
-extern "C" size_t hsr_capacity(int N, size_t inputSize)
+extern "C" size_t hsr_capacity(int family, int N, size_t inputSize)
 {
-  // src/rANS32x32_16w.cpp:10-13: buffer + histogram + state (+ one row of slack)
-  return inputSize + (size_t)N + sizeof(uint16_t) * 256 + sizeof(uint32_t) * (size_t)N + sizeof(uint64_t) * 2;
+  const size_t n = (size_t)N;
+  if (family == HSR_RAW) // src/rANS32x32_16w.cpp:10-13: buffer + one row of slack + histogram + states + lengths
+    return inputSize + n + sizeof(uint16_t) * 256 + sizeof(uint32_t) * n + sizeof(uint64_t) * 2;
+  // src/block_rANS32x32_16w_encode.cpp:47-54 / src/mt_rANS32x64_16w_encode.cpp:50-57: one header per possible
+  // block of MinMinBlockSize = 2^15 symbols; mt_ headers also carry the skip offset and a state snapshot
+  const size_t base = 2 * sizeof(uint64_t) + 256 * sizeof(uint16_t) + inputSize + n * sizeof(uint32_t);
+  const size_t blockCount = (inputSize + ((size_t)1 << 15)) / ((size_t)1 << 15) + 1;
+  const size_t perBlock = family == HSR_MT ? sizeof(uint64_t) * 2 + 256 * sizeof(uint16_t) + n * sizeof(uint32_t)
+                                           : sizeof(uint64_t) + 256 * sizeof(uint16_t);
+  return base + blockCount * perBlock;
 }
 
 extern "C" void *hsr_host_alloc(size_t bytes)
@@ -165,13 +173,17 @@ extern "C" long hsr_mt_index(int N, const uint8_t *in, size_t inLength, hsr_bloc
       if (pos + 16 + 4 * (uint64_t)N + 512 > inLength) { set_err("mt_ block header runs past the input"); return -1; }
       const uint64_t skip = rd64(in + pos + 8);
       if (skip >= (inLength - (pos + 16)) / 2) { set_err("mt_ skip offset runs past the input"); return -1; }
-      const uint64_t after = pos + 16 + 2 * (skip + 1); // :59
-      if (after < pos + 16 + 4 * (uint64_t)N + 512 || after > inLength) { set_err("mt_ skip offset inconsistent"); return -1; }
-      if (after - pos > kMaxUnitIn) { set_err("mt_ block larger than 4 GiB compressed is not supported"); return -1; }
+      uint64_t after = pos + 16 + 2 * (skip + 1); // :59
       uint64_t end = i + v; // :77-82
       if (end > outLengthInStates) end = outLengthInStates;
       else if (end & (uint64_t)(N - 1)) { set_err("mt_ block end not a multiple of the state count"); return -1; }
       const uint64_t rows = end > i ? (end - i + N - 1) / N : 0;
+      // The encoder measures the first block it writes (the LAST of the chain) from its last word slot rather
+      // than one past it (src/mt_rANS32x64_16w_encode.cpp:163,279), so that block's skip is 2 bytes short and
+      // nothing reads it; its words simply run to the end of the stream.
+      if (!(i + rows * N < outLengthInStates)) after = inLength;
+      if (after < pos + 16 + 4 * (uint64_t)N + 512 || after > inLength) { set_err("mt_ skip offset inconsistent"); return -1; }
+      if (after - pos > kMaxUnitIn) { set_err("mt_ block larger than 4 GiB compressed is not supported"); return -1; }
       hsr_block_t b{};
       b.inOffset = pos + 16; b.inEnd = after; b.outOffset = i; b.count = rows * N; b.kind = 0;
       lastCoded = (long)count;
@@ -327,12 +339,13 @@ __global__ void mt_walk_kernel(const uint8_t *in, uint64_t inLength, uint32_t N,
     } else {
       if (pos + 16 + 4ull * N + 512 > inLength) { err = 4; break; }
       if (skip >= (inLength - (pos + 16)) / 2) { err = 5; break; }
-      const uint64_t after = pos + 16 + 2 * (skip + 1);
-      if (after < pos + 16 + 4ull * N + 512 || after > inLength || after - pos > kMaxUnitIn) { err = 6; break; }
+      uint64_t after = pos + 16 + 2 * (skip + 1);
       uint64_t end = i + v;
       if (end > outLengthInStates) end = outLengthInStates;
       else if (end & (uint64_t)(N - 1)) { err = 7; break; }
       const uint64_t rows = end > i ? (end - i + N - 1) / N : 0;
+      if (!(i + rows * N < outLengthInStates)) after = inLength; // last block: see hsr_mt_index
+      if (after < pos + 16 + 4ull * N + 512 || after > inLength || after - pos > kMaxUnitIn) { err = 6; break; }
       if (lane == 0 && count < maxBlocks) {
         hsr_block_t b{};
         b.inOffset = pos + 16; b.inEnd = after; b.outOffset = i; b.count = rows * N; b.kind = 0;

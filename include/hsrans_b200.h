@@ -46,10 +46,10 @@ const char *hsr_last_error(void);
 int hsr_set_option(const char *key, long value);
 long hsr_get_option(const char *key);
 
-/* Worst-case compressed size for n input bytes; identical for all three framings.
+/* Worst-case compressed size for n input bytes (the buffer size a harness must allocate).
  * Replaces rANS32x32_16w_capacity (src/rANS32x32_16w.cpp:10-13), block_rANS32x32_16w_capacity
  * (src/block_rANS32x32_16w_encode.cpp:47-54), mt_rANS32x64_16w_capacity (src/mt_rANS32x64_16w_encode.cpp:50-57). */
-size_t hsr_capacity(int stateCount, size_t inputSize);
+size_t hsr_capacity(int family, int stateCount, size_t inputSize);
 
 /* Page-locked host buffers for the harness (the reference harness allocates 64-byte aligned buffers,
  * src/main.cpp:649-650). hsr_decode accepts any host pointer; pinned ones avoid a staging copy. */

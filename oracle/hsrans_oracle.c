@@ -149,9 +149,16 @@ uint32_t hsro_idx2idx(uint32_t j)
   return (j & ~31u) | (l & 3u) | ((l & 4u) << 2) | ((l & 24u) >> 1);
 }
 
-size_t hsro_capacity(uint32_t N, size_t inputSize)
+size_t hsro_capacity(uint32_t family, uint32_t N, size_t inputSize)
 {
-  return inputSize + N + sizeof(uint16_t) * 256 + sizeof(uint32_t) * N + sizeof(uint64_t) * 2;
+  if (family == HSRO_RAW)
+    return inputSize + N + sizeof(uint16_t) * 256 + sizeof(uint32_t) * N + sizeof(uint64_t) * 2;
+  const size_t minMinBlockSize = (size_t)1 << 15; /* src/block_rANS32x32_16w_encode.cpp:12-13 */
+  const size_t baseSize = 2 * sizeof(uint64_t) + 256 * sizeof(uint16_t) + inputSize + N * sizeof(uint32_t);
+  const size_t blockCount = (inputSize + minMinBlockSize) / minMinBlockSize + 1;
+  const size_t perBlock = family == HSRO_MT ? sizeof(uint64_t) * 2 + 256 * sizeof(uint16_t) + N * sizeof(uint32_t)
+                                            : sizeof(uint64_t) + 256 * sizeof(uint16_t);
+  return baseSize + blockCount * perBlock;
 }
 
 typedef struct dec_state {
@@ -436,7 +443,7 @@ size_t hsro_encode_raw(uint32_t N, uint32_t bits, const uint8_t *in, size_t leng
 {
   if (!(N == 32 || N == 64) || bits < 10 || bits > 15 || length == 0)
     return 0;
-  if (outCapacity < hsro_capacity(N, length)) /* src/rANS32x32_16w.cpp:37 */
+  if (outCapacity < hsro_capacity(HSRO_RAW, N, length)) /* src/rANS32x32_16w.cpp:37 */
     return 0;
   const uint32_t emitPoint = (CONSUME_POINT16 >> bits) << 16; /* :41 */
   uint32_t states[64];

@@ -46,7 +46,7 @@ def oracle() -> C.CDLL:
         lib.hsro_encode_raw.restype = sz
         lib.hsro_encode_raw.argtypes = [u32, u32, vp, sz, vp, sz, C.POINTER(OracleHist)]
         lib.hsro_capacity.restype = sz
-        lib.hsro_capacity.argtypes = [u32, sz]
+        lib.hsro_capacity.argtypes = [u32, u32, sz]
         lib.hsro_make_hist.restype = None
         lib.hsro_make_hist.argtypes = [C.POINTER(OracleHist), vp, sz, u32]
         lib.hsro_normalize_hist.restype = None
@@ -102,8 +102,8 @@ def _u8(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.uint8)
 
 
-def oracle_capacity(states: int, n: int) -> int:
-    return oracle().hsro_capacity(states, n)
+def oracle_capacity(family: int, states: int, n: int) -> int:
+    return oracle().hsro_capacity(family, states, n)
 
 
 def oracle_make_hist(data, bits: int):
@@ -124,7 +124,7 @@ def oracle_encode_raw(states: int, bits: int, data) -> np.ndarray:
     d = _u8(data)
     h = OracleHist()
     oracle().hsro_make_hist(C.byref(h), d.ctypes.data, d.size, bits)
-    cap = oracle_capacity(states, d.size)
+    cap = oracle_capacity(RAW, states, d.size)
     out = np.zeros(cap, np.uint8)
     n = oracle().hsro_encode_raw(states, bits, d.ctypes.data, d.size, out.ctypes.data, cap, C.byref(h))
     if n == 0:

@@ -1,0 +1,234 @@
+"""GPU (-m gpu): the CUDA path, called through the C-ABI, against the oracle / the reference — bit-exact.
+
+Nothing here reads /root/reference: streams come from the committed golden fixtures or from the reference build
+that travels in oracle/_ref/ (falling back to the oracle's raw encoder twin when that is absent)."""
+import numpy as np
+import pytest
+
+import checkers as ck
+from conftest import golden_stream_cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(pkg):
+    if pkg.device_count() < 1:
+        pytest.fail("no CUDA device: the -m gpu tests must run on the B200 box")
+    return pkg
+
+
+def _check(gpu, fam, states, bits, stream, data, label=""):
+    n, out = gpu.decode(fam, states, bits, stream, data.size)
+    assert n == data.size, (label, fam, states, bits, n, gpu.last_error())
+    if not np.array_equal(out[:n], data):
+        bad = np.nonzero(out[:n] != data)[0]
+        pytest.fail(f"{label} fam {fam} N {states} bits {bits}: {bad.size} wrong bytes, first at {bad[:8]}")
+    assert out[n:].size == 0 or np.all(out[n:] == 0xCC)  # never writes past the decoded length
+
+
+@pytest.mark.parametrize("table", [0, 1])
+def test_golden_streams_bit_exact(gpu, golden, table):
+    gpu.set_option("table", table)
+    try:
+        cases = golden_stream_cases(golden)
+        for name, fam, states, bits, stream, ret, data in cases:
+            if ret == 0:
+                assert gpu.decode(fam, states, bits, stream, data.size)[0] == 0, (name, fam, states, bits)
+                continue
+            _check(gpu, fam, states, bits, stream, data, name)
+    finally:
+        gpu.set_option("table", 0)
+
+
+def _zipf(pkg, n, s, seed, seg):
+    return pkg.synth_zipf(n, s, seed=seed, segment_bytes=seg)
+
+
+@pytest.mark.parametrize("fam", [ck.RAW, ck.BLOCK, ck.MT])
+def test_fresh_streams_all_bits_and_ragged_lengths(gpu, fam):
+    if fam != ck.RAW and not ck.have_ref():
+        pytest.skip("block_/mt_ stream production needs oracle/_ref")
+    lengths = [64, 65, 95, 127, 128, 4097, 70_001, 1_000_031]
+    seed = 100
+    for states in (32, 64):
+        for bits in range(10, 16):
+            n = lengths[(bits + states) % len(lengths)]
+            for n in {n, lengths[(bits * 3 + states // 32) % len(lengths)]}:
+                seed += 1
+                data = _zipf(gpu, n, 1.0, seed, 65536 if seed % 2 else 0)
+                stream = ck.encode(fam, states, bits, data)
+                _check(gpu, fam, states, bits, stream, data, f"n={n}")
+                on, oo = ck.oracle_decode(fam, states, bits, stream, n)
+                assert on == n and np.array_equal(oo[:n], data)
+
+
+@pytest.mark.parametrize("s", [0.0, 0.5, 1.5, 3.0])
+def test_entropy_sweep(gpu, s):
+    """BASELINE config 5: near-uniform to highly skewed sources, raw vs block_ (per-block normalised) histograms."""
+    n = 600_011
+    data = _zipf(gpu, n, s, 77, 65536)
+    for fam in (ck.RAW, ck.BLOCK, ck.MT):
+        if fam != ck.RAW and not ck.have_ref():
+            continue
+        for states, bits in ((32, 10), (64, 12), (32, 13), (64, 15)):
+            stream = ck.encode(fam, states, bits, data)
+            _check(gpu, fam, states, bits, stream, data, f"s={s}")
+
+
+def test_single_symbol_runs_and_constant_input(gpu, golden):
+    for key in ("stream/runs/2/64/11", "stream/runs/2/32/14", "stream/runs/1/32/12", "stream/runs/1/64/15"):
+        _, name, fam, states, bits = key.split("/")
+        _check(gpu, int(fam), int(states), int(bits), golden[key], golden["in/runs"], key)
+    const = golden["in/const"]
+    _check(gpu, ck.RAW, 32, 11, golden["stream/const/0/32/11"], const, "const raw 11")
+    _check(gpu, ck.RAW, 64, 15, golden["stream/const/0/64/15"], const, "const raw 15")
+    # freq == 2^12 does not fit the reference's packed 12-bit field (src/hist.cpp:304); ours must still decode it
+    data = np.full(9000, 0x21, np.uint8)
+    stream = ck.oracle_encode_raw(64, 12, data)
+    _check(gpu, ck.RAW, 64, 12, stream, data, "const raw 12")
+
+
+def test_malformed_streams_return_zero(gpu, golden):
+    n = golden["in/multi"].size
+    mt = golden["stream/multi/2/64/15"]
+    bad = mt.copy(); bad[16 + 16 + 256 + 9] ^= 0x20          # first block's histogram no longer sums to 2^15
+    assert gpu.decode(ck.MT, 64, 15, bad, n)[0] == 0
+    assert "status" in gpu.last_error()
+    blk = golden["stream/multi/1/32/10"]
+    bad = blk.copy(); bad[16 + 128 + 8 + 5] ^= 0x10
+    assert gpu.decode(ck.BLOCK, 32, 10, bad, n)[0] == 0
+    raw = golden["stream/multi/0/64/12"]
+    bad = raw.copy(); bad[16 + 3] ^= 0x01
+    assert gpu.decode(ck.RAW, 64, 12, bad, n)[0] == 0
+    assert gpu.decode(ck.RAW, 64, 12, raw, n - 1)[0] == 0     # outCapacity too small
+    # and a good stream still decodes afterwards
+    _check(gpu, ck.RAW, 64, 12, raw, golden["in/multi"], "after errors")
+
+
+def test_prepared_stream_device_api_and_shards(gpu, golden):
+    import torch
+    data = golden["in/multi"]
+    stream = golden["stream/multi/2/64/15"]
+    n = data.size
+    out = torch.full((n + 64,), 0xCC, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ps = gpu.PreparedStream.upload(ck.MT, 64, 15, stream)
+    assert ps.decoded_length == n and ps.units >= 4 and ps.shard_out_bytes == n
+    assert ps.decode_async(out.data_ptr(), n, st) >= 1
+    torch.cuda.synchronize()
+    assert ps.status() == 0
+    assert np.array_equal(out[:n].cpu().numpy(), data) and bool((out[n:] == 0xCC).all())
+    ps.free()
+    # three shards decoded into the same device buffer tile it exactly
+    out.fill_(0xCC)
+    total = 0
+    for r in range(3):
+        sh = gpu.PreparedStream.upload(ck.MT, 64, 15, stream, shard=r, shards=3)
+        total += sh.shard_out_bytes
+        sh.decode_async(out.data_ptr(), n, st)
+        torch.cuda.synchronize()
+        assert sh.status() == 0
+        # shard-local output: only this rank's bytes, based at 0
+        loc = torch.full((sh.shard_out_bytes + 16,), 0xCC, dtype=torch.uint8, device="cuda")
+        sh.decode_async(loc.data_ptr(), sh.shard_out_bytes, st, shard_local=True)
+        torch.cuda.synchronize()
+        lo = sh.shard_out_offset
+        assert np.array_equal(loc[: sh.shard_out_bytes].cpu().numpy(), data[lo: lo + sh.shard_out_bytes])
+        sh.free()
+    assert total == n and np.array_equal(out[:n].cpu().numpy(), data)
+    # stream that only exists in device memory: the chain is walked by a kernel
+    dev_in = torch.from_numpy(stream.copy()).cuda()
+    ds = gpu.PreparedStream.from_device(ck.MT, 64, 15, dev_in.data_ptr(), stream.size)
+    host_idx = gpu.mt_index(64, stream)
+    dev_idx = ds.index()
+    assert len(dev_idx) == len(host_idx)
+    for a, b in zip(dev_idx, host_idx):
+        assert (a.inOffset, a.inEnd, a.outOffset, a.count, a.kind, a.symbol, a.tail) == \
+               (b.inOffset, b.inEnd, b.outOffset, b.count, b.kind, b.symbol, b.tail)
+    out.fill_(0xCC)
+    ds.decode_async(out.data_ptr(), n, st)
+    torch.cuda.synchronize()
+    assert ds.status() == 0 and np.array_equal(out[:n].cpu().numpy(), data)
+    ds.free()
+    for fam, states, bits in ((ck.RAW, 64, 12), (ck.BLOCK, 32, 10)):
+        s2 = golden[f"stream/multi/{fam}/{states}/{bits}"]
+        p2 = gpu.PreparedStream.upload(fam, states, bits, s2)
+        out.fill_(0xCC)
+        p2.decode_async(out.data_ptr(), n, st)
+        torch.cuda.synchronize()
+        assert p2.status() == 0 and np.array_equal(out[:n].cpu().numpy(), data)
+        p2.free()
+
+
+def test_multi_device_entry_point_on_one_gpu(gpu, golden):
+    data = golden["in/multi"]
+    n, out = gpu.decode_mt_multi(64, 15, golden["stream/multi/2/64/15"], data.size, devices=[0, 0])
+    assert n == data.size and np.array_equal(out[:n], data)
+
+
+def test_pinned_host_buffers(gpu, golden):
+    data = golden["in/multi"]
+    stream = golden["stream/multi/2/32/12"]
+    hin, hout = gpu.host_alloc(stream.size), gpu.host_alloc(data.size)
+    hin.array[:] = stream
+    hout.array[:] = 0xCC
+    n, out = gpu.decode(ck.MT, 32, 12, hin.array, data.size, out=hout.array)
+    assert n == data.size and np.array_equal(out, data)
+    hin.free(); hout.free()
+
+
+def test_device_histogram_bit_exact(gpu, golden):
+    for key in golden:
+        if not key.startswith("hist/"):
+            continue
+        _, name, bits = key.split("/")
+        cnt, cum = gpu.make_hist(golden[f"in/{name}"], int(bits))
+        assert np.array_equal(cnt, golden[key][0]) and np.array_equal(cum, golden[key][1]), key
+    data = _zipf(gpu, 3_000_001, 1.0, 5, 65536)
+    for bits in (10, 12, 15):
+        want = ck.oracle_make_hist(data, bits)
+        got = gpu.make_hist(data, bits)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
+def test_device_segment_histograms(gpu):
+    import torch
+    data = _zipf(gpu, 1_000_000, 1.2, 9, 65536)
+    seg = 65536
+    nseg = (data.size + seg - 1) // seg
+    d = torch.from_numpy(data).cuda()
+    counts = torch.zeros((nseg, 256), dtype=torch.int16, device="cuda")
+    for bits in (10, 15):
+        assert gpu.make_hist_segments_device(d.data_ptr(), data.size, seg, bits, counts.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream) > 0
+        torch.cuda.synchronize()
+        got = counts.cpu().numpy().view(np.uint16)
+        for k in range(nseg):
+            want, _ = ck.oracle_make_hist(data[k * seg:(k + 1) * seg], bits)
+            assert np.array_equal(got[k], want), (bits, k)
+
+
+def test_observe_hist_device_counts(gpu):
+    import torch
+    data = _zipf(gpu, 5_000_003, 1.0, 11, 0)
+    d = torch.from_numpy(data).cuda()
+    hist = torch.zeros(256, dtype=torch.int32, device="cuda")
+    # deliberately misaligned start
+    assert gpu.observe_hist_device(d.data_ptr() + 3, data.size - 3, hist.data_ptr(), torch.cuda.current_stream().cuda_stream) > 0
+    torch.cuda.synchronize()
+    assert np.array_equal(hist.cpu().numpy().astype(np.int64), np.bincount(data[3:], minlength=256))
+
+
+def test_full_size_100mb_round_trip(gpu):
+    """BASELINE.json sizes: 100,000,000-byte Zipf stream; decode(encode(x)) == x for configs 1-3 and the mt_ codec."""
+    n = 100_000_000
+    data = _zipf(gpu, n, 1.0, 42, 65536)
+    cases = [(ck.RAW, 64, 12)]
+    if ck.have_ref():
+        cases += [(ck.MT, 64, 15), (ck.BLOCK, 32, 10), (ck.RAW, 32, 11)]
+    for fam, states, bits in cases:
+        stream = ck.encode(fam, states, bits, data)
+        n_out, out = gpu.decode(fam, states, bits, stream, n)
+        assert n_out == n, gpu.last_error()
+        assert np.array_equal(out[:n], data), (fam, states, bits)

@@ -1,0 +1,93 @@
+"""CPU: the oracle (oracle/hsrans_oracle.c) against vectors produced by the unmodified reference."""
+import numpy as np
+import pytest
+
+import checkers as ck
+from conftest import golden_stream_cases
+
+
+def test_oracle_decodes_every_golden_stream(golden):
+    cases = golden_stream_cases(golden)
+    assert len(cases) > 200
+    for name, fam, states, bits, stream, ret, data in cases:
+        n, out = ck.oracle_decode(fam, states, bits, stream, data.size)
+        assert n == ret, (name, fam, states, bits, n, ret)
+        if ret:
+            assert np.array_equal(out[:n], data), (name, fam, states, bits)
+            # capacity one byte short -> 0 (src/rANS32x32_16w.cpp:173)
+            n2, _ = ck.oracle_decode(fam, states, bits, stream, data.size - 1)
+            assert n2 == 0
+
+
+def test_oracle_raw_encoder_twin_is_byte_identical(golden):
+    hit = 0
+    for name, fam, states, bits, stream, ret, data in golden_stream_cases(golden):
+        if fam != ck.RAW:
+            continue
+        mine = ck.oracle_encode_raw(states, bits, data)
+        assert np.array_equal(mine, stream), (name, states, bits)
+        hit += 1
+    assert hit >= 60
+
+
+def test_oracle_make_hist_matches_reference(golden):
+    for key in golden:
+        if not key.startswith("hist/"):
+            continue
+        _, name, bits = key.split("/")
+        cnt, cum = ck.oracle_make_hist(golden[f"in/{name}"], int(bits))
+        assert np.array_equal(cnt, golden[key][0]) and np.array_equal(cum, golden[key][1]), key
+        assert int(cnt.astype(np.int64).sum()) == 1 << int(bits)
+
+
+def test_oracle_normalize_with_foreign_data_bytes(golden):
+    hist = golden["norm/safe/hist"]
+    extra = int((np.bincount(golden["in/multi"][:65536], minlength=256) == 0).sum())
+    for bits in range(10, 16):
+        cnt, cum = ck.oracle_normalize_hist(hist, 65536 + extra, bits)
+        want = golden[f"norm/safe/{bits}"]
+        assert np.array_equal(cnt, want[0]) and np.array_equal(cum, want[1]), bits
+
+
+def test_idx2idx_closed_form():
+    table32 = [0x00, 0x01, 0x02, 0x03, 0x10, 0x11, 0x12, 0x13, 0x04, 0x05, 0x06, 0x07, 0x14, 0x15, 0x16, 0x17,
+               0x08, 0x09, 0x0A, 0x0B, 0x18, 0x19, 0x1A, 0x1B, 0x0C, 0x0D, 0x0E, 0x0F, 0x1C, 0x1D, 0x1E, 0x1F]
+    for j in range(64):  # src/block_codec64.h:22-28: second half is the first + 32
+        assert ck.oracle().hsro_idx2idx(j) == table32[j % 32] + 32 * (j // 32)
+
+
+def test_oracle_rejects_corrupt_streams(golden):
+    stream = golden["stream/small/2/64/12"].copy()
+    n = golden["in/small"].size
+    assert ck.oracle_decode(ck.MT, 64, 12, stream[:100], n)[0] == 0          # shorter than the fixed header
+    bad = stream.copy(); bad[16 + 16 + 256 + 10] ^= 0x40                      # break the histogram sum
+    assert ck.oracle_decode(ck.MT, 64, 12, bad, n)[0] == 0
+    bad = stream.copy(); bad[8:16] = np.frombuffer(np.uint64(stream.size + 1).tobytes(), np.uint8)
+    assert ck.oracle_decode(ck.MT, 64, 12, bad, n)[0] == 0                     # claims more input than given
+    raw = golden["stream/small/0/32/11"].copy(); raw[16 + 7] ^= 1
+    assert ck.oracle_decode(ck.RAW, 32, 11, raw, n)[0] == 0
+
+
+@pytest.mark.skipif(not ck.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+def test_oracle_vs_compiled_reference_on_fresh_inputs():
+    rng = np.random.default_rng(2026)
+    for trial in range(6):
+        n = int(rng.integers(64, 400_000))
+        s = float(rng.choice([0.0, 0.7, 1.0, 1.6, 2.5]))
+        p = 1.0 / np.arange(1, 257) ** s
+        p /= p.sum()
+        data = rng.permutation(256).astype(np.uint8)[rng.choice(256, n, p=p)]
+        if trial % 2:
+            seg = 65536
+            for o in range(0, n, seg):
+                data[o:o + seg] = rng.permutation(256).astype(np.uint8)[data[o:o + seg]]
+        for fam in (ck.RAW, ck.BLOCK, ck.MT):
+            states = int(rng.choice([32, 64]))
+            bits = int(rng.integers(10, 16))
+            stream = ck.ref_encode(fam, states, bits, data)
+            n_ref, out_ref = ck.ref_decode(fam, states, bits, stream, n, ck.IMPL_AVX2 if fam == ck.RAW else 0)
+            n_or, out_or = ck.oracle_decode(fam, states, bits, stream, n)
+            assert n_ref == n_or == n, (fam, states, bits, n, n_ref, n_or)
+            assert np.array_equal(out_or[:n], out_ref[:n]) and np.array_equal(out_or[:n], data)
+        for bits in (10, 13, 15):
+            assert all(np.array_equal(a, b) for a, b in zip(ck.oracle_make_hist(data, bits), ck.ref_make_hist(data, bits)))
