@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--zipf", type=float, default=1.0)
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-only", action="store_true", help="skip e2e / index / CPU legs (profiling runs)")
+    ap.add_argument("--table", type=int, default=0, help="hsr_set_option table: 0 auto, 1 bitmap-rank, 2 packed")
     ap.add_argument("--extra", action="store_true", help="also report BASELINE configs 2 and 3 (single-recurrence codecs)")
     return ap.parse_args()
 
@@ -273,6 +275,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    pkg.set_option("table", a.table)
     data, stream, enc_s = make_input(pkg, a, rank)
     n = data.size
     comp = stream.size
@@ -302,6 +305,13 @@ def main():
     ms_per_step = total_ms / a.steps
     value = world * n / (ms_per_step * 1e-3) / 1e9
     clocks = clk.summary()
+
+    if a.kernel_only:
+        if rank == 0:
+            print(json.dumps({"kernel_only": True, "value": round(value, 3), "unit": "GB/s", "ms_per_step": round(ms_per_step, 4),
+                              "bits": a.bits, "states": a.states, "table": a.table, "blocks": int(units), "compressed": comp,
+                              "traffic_GBps": round((comp + n) / (ms_per_step * 1e-3) / 1e9, 1), "clocks": clocks}), flush=True)
+        return
 
     # ---------------------------------------------------------------- end to end through the drop-in host call
     e2e_steps = a.e2e_steps or min(a.steps, 10)

@@ -241,28 +241,27 @@ struct LaunchInfo {
 
 static std::mutex g_attrMutex;
 
-// opt in to > 48 KB dynamic shared memory and query residency, once per (kernel, device)
-static bool prepare_kernel(const void *fn, int smemBytes, int threads, LaunchInfo *li)
+// residency of a one-warp-CTA kernel, queried once per (kernel, device)
+static bool prepare_kernel(const void *fn, LaunchInfo *li)
 {
-  struct Key { const void *fn; int dev; int smem; LaunchInfo li; };
+  struct Key { const void *fn; int dev; LaunchInfo li; };
   static std::vector<Key> cache;
   int dev = 0;
   CU_TRY(cudaGetDevice(&dev), return false);
   std::lock_guard<std::mutex> lock(g_attrMutex);
   for (auto &k : cache)
-    if (k.fn == fn && k.dev == dev && k.smem == smemBytes) { *li = k.li; return true; }
-  CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes), return false);
+    if (k.fn == fn && k.dev == dev) { *li = k.li; return true; }
   CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), return false);
   LaunchInfo out;
-  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out.ctasPerSm, fn, threads, smemBytes), return false);
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out.ctasPerSm, fn, 32, 0), return false);
   CU_TRY(cudaDeviceGetAttribute(&out.smCount, cudaDevAttrMultiProcessorCount, dev), return false);
-  if (out.ctasPerSm < 1) { set_err("kernel does not fit on an SM with %d bytes of shared memory", smemBytes); return false; }
-  cache.push_back({fn, dev, smemBytes, out});
+  if (out.ctasPerSm < 1) { set_err("kernel does not fit on an SM"); return false; }
+  cache.push_back({fn, dev, out});
   *li = out;
   return true;
 }
 
-// launches the units kernel over blocks [first, first+count) of a device-resident index
+// launches the units kernel over `numBlocks` records of a device-resident index
 static int launch_units(int N, int bits, const uint8_t *dIn, uint64_t inBase, uint8_t *dOut, uint64_t outBase,
                         const hsr_block_t *dBlocks, uint32_t numBlocks, uint32_t *dCounter, cudaStream_t st)
 {
@@ -273,17 +272,12 @@ static int launch_units(int N, int bits, const uint8_t *dIn, uint64_t inBase, ui
   void *args[] = {&p};
   CU_TRY(cudaMemsetAsync(dCounter, 0, 4, st), return -1); // work counter only; status bits accumulate
   LaunchInfo li;
-  if (numBlocks == 1) {
-    if (!prepare_kernel(ke.unitsW1, ke.warpBytes, 32, &li)) return -1;
-    CU_TRY(cudaLaunchKernel(ke.unitsW1, dim3(1), dim3(32), args, (size_t)ke.warpBytes, st), return -1);
-    return 1;
-  }
-  const int warps = 4;
-  const int smem = ke.warpBytes * warps;
-  if (!prepare_kernel(ke.unitsW4, smem, warps * 32, &li)) return -1;
-  const uint32_t want = (numBlocks + warps - 1) / warps;
-  const uint32_t grid = std::min<uint32_t>(want, (uint32_t)(li.ctasPerSm * li.smCount));
-  CU_TRY(cudaLaunchKernel(ke.unitsW4, dim3(grid), dim3(warps * 32), args, (size_t)smem, st), return -1);
+  if (!prepare_kernel(ke.units, &li)) return -1;
+  // persistent one-warp CTAs: every SM filled to its residency limit, units handed out by an atomic counter
+  const long optWarps = g_optWarps;
+  const uint32_t perSm = optWarps > 0 ? std::min<uint32_t>((uint32_t)optWarps, (uint32_t)li.ctasPerSm) : (uint32_t)li.ctasPerSm;
+  const uint32_t grid = std::min<uint32_t>(numBlocks, perSm * (uint32_t)li.smCount);
+  CU_TRY(cudaLaunchKernel(ke.units, dim3(grid), dim3(32), args, 0, st), return -1);
   return 1;
 }
 
@@ -294,9 +288,7 @@ static int launch_block_stream(int N, int bits, const uint8_t *dIn, uint64_t inL
   const KernelEntry &ke = kernel_entry(N, bits, table);
   BlockStreamParams p{dIn, inLength, dOut, n, dCounter};
   void *args[] = {&p};
-  LaunchInfo li;
-  if (!prepare_kernel(ke.block, ke.warpBytes, 32, &li)) return -1;
-  CU_TRY(cudaLaunchKernel(ke.block, dim3(1), dim3(32), args, (size_t)ke.warpBytes, st), return -1);
+  CU_TRY(cudaLaunchKernel(ke.block, dim3(1), dim3(32), args, 0, st), return -1);
   return 1;
 }
 

@@ -9,15 +9,18 @@
 // The AVX movemask/popcnt + shuffle-LUT word hand-out (src/rANS32x32_16w.cpp:1229-1290) becomes
 // __ballot_sync + __popc(mask & lanemask_lt) on a warp-wide word cursor.
 //
-// Shared-memory tables (private layouts; only the decoded bytes have to match the reference):
-//   TK_RANK   bitmap-rank table, any bits: one u32 per 16 slots {8*starts_before_group : 16 | start_bitmap : 16}
-//             and one 8-byte entry per present symbol {freq - 2^b, (-cumul) << 8 | symbol}.  2^(b-2) + 2 KB
-//             (10 KB at 15 bits vs 33 KB for the reference's hist_dec2_t, src/hist.h:32-37) and O(256 + 2^b/16)
-//             to build instead of O(2^b).
-//   TK_PACKED one u32 per slot {freq : 12 | slot - cumul : 12 | symbol : 8}, bits <= 12, one lookup on the chain
+// One CTA = one warp, so every table lives at a compile-time shared-memory address and lookups are
+// LDS [reg + imm]. Shared-memory tables (private layouts; only the decoded bytes have to match the reference):
+//   TK_RANK   bitmap-rank table, any bits:
+//               grp[2^b / 16]  u32  {4 * (symbol starts before this group) : 16 | start bitmap of its 16 slots : 16}
+//               ent[256]       u32  per PRESENT symbol, in slot order {-cumul : 16 | 2^b - freq : 16}
+//               sym[256]       u8   rank -> symbol (skipped when all 256 symbols are present: rank == symbol)
+//             2^(b-2) + 1.25 KB (9.25 KB at 15 bits vs 33 KB for the reference's hist_dec2_t, src/hist.h:32-37)
+//             and O(256 + 2^b/16) to build instead of O(2^b).
+//   TK_PACKED one u32 per slot {freq : 12 | symbol : 8 | slot - cumul : 12}, bits <= 12, one lookup on the chain
 //             (the reference's hist_dec_pack_t idea, src/hist.h:46-50, with the bias pre-subtracted).
-// Compressed words are staged by cp.async (LDGSTS, 16 B per lane) into a per-warp ring of overlapping linear
-// segments, so the data-dependent word reads are LDS, never exposed DRAM latency.
+// Compressed words are staged by cp.async (LDGSTS, 16 B per lane) into a ring of overlapping linear segments, so
+// the data-dependent word reads are LDS, never exposed DRAM latency.
 #pragma once
 
 #include <cstdint>
@@ -51,13 +54,24 @@ __device__ __forceinline__ uint32_t ldg_u16(const uint8_t *p) { return __ldg(rei
 __device__ __forceinline__ uint32_t ldg_u32_a2(const uint8_t *p) { return ldg_u16(p) | (ldg_u16(p + 2) << 16); }
 __device__ __forceinline__ uint64_t ldg_u64_a2(const uint8_t *p) { return (uint64_t)ldg_u32_a2(p) | ((uint64_t)ldg_u32_a2(p + 4) << 32); }
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// The CTA's shared memory is declared in PTX, not C++: `mov.u32 r, hsr_smem_arr` is then a link-time constant,
+// ptxas keeps it in a uniform register and every table lookup becomes LDS [reg + UR + imm] with no address
+// arithmetic. (A C++ __shared__ array reached through generic pointers drags the cluster shared-window base,
+// S2R SR_CgaCtaId + LEA, and one extra IADD per lookup through the hot loop.) Call exactly once per kernel.
+template <int BYTES>
+__device__ __forceinline__ uint32_t declare_smem()
+{
+  uint32_t base;
+  asm volatile(".shared .align 16 .b8 hsr_smem_arr[%1];\n\tmov.u32 %0, hsr_smem_arr;" : "=r"(base) : "n"(BYTES));
+  return base;
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint2 lds_u64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts_u64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_v4(uint32_t a, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+__device__ __forceinline__ void atoms_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t srcBytes)
 {
@@ -80,7 +94,8 @@ struct WarpLayout {
   static constexpr int kSlots = 1 << BITS;
   static constexpr int kGroups = kSlots / 16;       // bitmap-rank groups of 16 slots
   static constexpr int kGrpBytes = kGroups * 4;
-  static constexpr int kEntBytes = 257 * 8 + 8;     // entries are indexed 1..256 (starts up to and including the slot)
+  static constexpr int kEntBytes = 256 * 4;
+  static constexpr int kSymBytes = 256;
   static constexpr int kPackedBytes = TK == TK_PACKED ? kSlots * 4 : 0;
 
   // word ring: kBufs linear segments of kSeg bytes; consecutive segments overlap by one worst-case row
@@ -92,10 +107,11 @@ struct WarpLayout {
 
   static constexpr int kOffGrp = 0;
   static constexpr int kOffEnt = kOffGrp + kGrpBytes;
-  static constexpr int kOffPacked = kOffEnt + kEntBytes;
+  static constexpr int kOffSym = kOffEnt + kEntBytes;
+  static constexpr int kOffPacked = kOffSym + kSymBytes;
   static constexpr int kOffRing = kOffPacked + kPackedBytes;
-  static constexpr int kBytes = kOffRing + kRingBytes; // per warp, multiple of 16
-  static_assert(kBytes % 16 == 0, "per-warp shared memory must stay 16-byte aligned");
+  static constexpr int kBytes = kOffRing + kRingBytes; // per warp (= per CTA), multiple of 16
+  static_assert(kBytes % 16 == 0 && kBytes <= 48 * 1024, "static shared memory budget");
 };
 
 // ---------------------------------------------------------------------------------------------- word ring
@@ -105,20 +121,21 @@ struct WarpLayout {
 // once cursor - k*kStride >= kStride, which is exactly where segment k+1 begins.
 template <class L>
 struct WordRing {
-  uint32_t sbuf;        // shared address of buffer 0
+  uint32_t sbuf;        // shared address of buffer 0 (constant)
   const uint8_t *gbase; // 16-byte aligned
   uint32_t glimit;      // readable bytes from gbase (never read past the caller's inLength)
   uint32_t seg;         // current segment
-  uint32_t segStart;    // seg * kStride
-  uint32_t cur;         // cursor, bytes from gbase
+  uint32_t wp;          // shared address of the word cursor (inside segment `seg`'s buffer)
+  uint32_t wlimit;      // leave the segment once wp reaches this (buffer start + kStride)
+
+  __device__ __forceinline__ uint32_t buf(uint32_t k) const { return sbuf + (k % L::kBufs) * L::kSeg; }
 
   __device__ __forceinline__ void issue(uint32_t k, uint32_t lane) const
   {
     const uint32_t srcOff = k * L::kStride + lane * 16u;
-    const uint32_t dst = sbuf + (k % L::kBufs) * L::kSeg + lane * 16u;
     uint32_t bytes = srcOff < glimit ? glimit - srcOff : 0u;
     bytes = bytes > 16u ? 16u : bytes;
-    cp_async16(dst, gbase + (bytes ? srcOff : 0u), bytes); // bytes == 0: pure zero fill, no global read
+    cp_async16(buf(k) + lane * 16u, gbase + (bytes ? srcOff : 0u), bytes); // bytes == 0: zero fill only
     cp_async_commit();
   }
 
@@ -127,11 +144,11 @@ struct WordRing {
     sbuf = sbuf_;
     const uintptr_t a = reinterpret_cast<uintptr_t>(firstWord);
     gbase = reinterpret_cast<const uint8_t *>(a & ~(uintptr_t)15);
-    cur = (uint32_t)(a & 15);
     const uint64_t avail = (uint64_t)(streamEnd - gbase);
     glimit = avail > 0xffffffffull ? 0xffffffffu : (uint32_t)avail;
     seg = 0;
-    segStart = 0;
+    wp = sbuf + (uint32_t)(a & 15);
+    wlimit = sbuf + L::kStride;
     __syncwarp(); // every lane is done with whatever lived in the ring before
 #pragma unroll
     for (uint32_t k = 0; k + 2 <= (uint32_t)L::kBufs; k++)
@@ -143,43 +160,54 @@ struct WordRing {
   // call once per row, before any word of the row is read
   __device__ __forceinline__ void advance_if_needed(uint32_t lane)
   {
-    if (cur - segStart >= (uint32_t)L::kStride) {
+    if (wp >= wlimit) {
+      const uint32_t into = wp - wlimit; // offset inside the next segment
       seg += 1;
-      segStart += L::kStride;
       issue(seg + L::kBufs - 2, lane); // lands in the buffer of segment seg-2, abandoned one segment ago
       cp_async_wait<L::kBufs - 2>();   // segment `seg` has landed for this lane ...
       __syncwarp();                    // ... and for all the others
+      const uint32_t b = buf(seg);
+      wp = b + into;
+      wlimit = b + L::kStride;
     }
   }
 
-  __device__ __forceinline__ uint32_t cursor_addr() const { return sbuf + (seg % L::kBufs) * L::kSeg + (cur - segStart); }
+  // bytes consumed from gbase so far
+  __device__ __forceinline__ uint32_t cursor() const { return seg * L::kStride + (wp - buf(seg)); }
 
   __device__ __forceinline__ void drain() const { cp_async_wait<0>(); }
 };
 
 // ---------------------------------------------------------------------------------------------- table build
 
-// Builds the warp's tables from 256 u16 counts at `counts` (2-byte aligned global memory).
-// Returns false (warp-uniform) unless the counts sum to 2^BITS (src/hist.cpp:308-324).
+struct TableInfo {
+  bool ok;          // counts sum to 2^BITS (src/hist.cpp:308-324)
+  bool allPresent;  // every symbol has a non-zero count: rank == symbol
+  bool degenerate;  // one symbol owns the whole range (freq == 2^BITS)
+};
+
+// Builds the warp's tables from 256 u16 counts at `counts` (2-byte aligned global memory). Warp-uniform result.
 template <int BITS, int N, int TK>
-__device__ __forceinline__ bool build_tables(uint8_t *smemWarp, const uint8_t *counts, uint32_t lane)
+__device__ __forceinline__ TableInfo build_tables(uint32_t smemWarp, const uint8_t *counts, uint32_t lane)
 {
   using L = WarpLayout<BITS, N, TK>;
-  const uint32_t sGrp = smem_u32(smemWarp + L::kOffGrp);
-  const uint32_t sEnt = smem_u32(smemWarp + L::kOffEnt);
+  const uint32_t sGrp = smemWarp + L::kOffGrp;
+  const uint32_t sEnt = smemWarp + L::kOffEnt;
+  const uint32_t sSym = smemWarp + L::kOffSym;
+  TableInfo info{false, false, false};
 
   // lane l owns symbols 8l .. 8l+7
   uint32_t freq[8];
-  uint32_t sum = 0, present = 0;
+  uint32_t sum = 0, present = 0, big = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     freq[k] = ldg_u16(counts + 2 * (lane * 8 + k));
     sum += freq[k];
     present += freq[k] != 0;
+    big |= freq[k] == (uint32_t)L::kSlots;
   }
-  // one inclusive scan carries both running totals: frequencies (<= 2^16 per lane... kept in the low 20 bits)
-  // and present-symbol counts (high 12 bits)
-  uint32_t packed = sum | (present << 20);
+  // one inclusive scan carries both running totals: frequencies (low 20 bits) and present-symbol counts (high 12)
+  const uint32_t packed = sum | (present << 20);
   uint32_t incl = packed;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -187,85 +215,73 @@ __device__ __forceinline__ bool build_tables(uint8_t *smemWarp, const uint8_t *c
     if (lane >= (uint32_t)d)
       incl += up;
   }
-  const uint32_t total = __shfl_sync(kFull, incl, 31) & 0xfffffu;
-  // a corrupt histogram can carry up to 256 * 65535 in the low field; 20 bits hold 2^20 - 1 < that, so check
-  // the per-lane sums for overflow as well
+  const uint32_t last = __shfl_sync(kFull, incl, 31);
+  // a corrupt histogram can carry up to 256 * 65535; per-lane sums above 2^BITS are rejected first so the
+  // 20-bit field cannot overflow unnoticed (32 * 2^15 = 2^20 wraps to 0 != 2^BITS)
   const bool laneOk = sum <= (uint32_t)L::kSlots;
-  if (!__all_sync(kFull, laneOk) || total != (uint32_t)L::kSlots)
-    return false;
+  if (!__all_sync(kFull, laneOk) || (last & 0xfffffu) != (uint32_t)L::kSlots)
+    return info;
+  info.ok = true;
+  info.allPresent = (last >> 20) == 256u;
+  info.degenerate = __any_sync(kFull, big != 0);
 
   __syncwarp();
-  // clear the bitmap groups
-  for (uint32_t o = lane * 16u; o < (uint32_t)L::kGrpBytes; o += 512u)
+  for (uint32_t o = lane * 16u; o < (uint32_t)L::kGrpBytes; o += 512u) // clear the bitmap groups
     sts_v4(sGrp + o, make_uint4(0, 0, 0, 0));
   __syncwarp();
 
-  uint32_t excl = incl - packed;
+  const uint32_t excl = incl - packed;
   uint32_t cumul = excl & 0xfffffu;
   uint32_t rank = excl >> 20; // present symbols before mine
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     if (freq[k]) {
-      // symbol start bit
-      atomicOr(reinterpret_cast<unsigned *>(smemWarp + L::kOffGrp) + (cumul >> 4), 1u << (cumul & 15u));
-      // entry index = number of starts at or below any slot of this symbol = rank + 1
-      const uint32_t sym = lane * 8u + (uint32_t)k;
-      const uint32_t fm = freq[k] - (uint32_t)L::kSlots;             // x' = (x >> b) * fm + x - cumul
-      const uint32_t w1 = ((0u - cumul) << 8) | sym;
-      sts_u64(sEnt + (rank + 1u) * 8u, make_uint2(fm, w1));
+      if (cumul) // the start at slot 0 is implicit, so that (starts before or at a slot) == rank of its symbol
+        atoms_or(sGrp + ((cumul >> 4) << 2), 1u << (cumul & 15u));
+      // x' = x + (x >> b) * (freq - 2^b) - cumul; both fields are signed 16-bit
+      const uint32_t e = (((0u - cumul) & 0xffffu) << 16) | ((freq[k] - (uint32_t)L::kSlots) & 0xffffu);
+      sts_u32(sEnt + rank * 4u, e);
+      sts_u8(sSym + rank, lane * 8u + (uint32_t)k);
       rank += 1;
       cumul += freq[k];
     }
   }
   __syncwarp();
 
-  // per-group prefix of start counts; lane owns kGroups/32 consecutive groups
-  constexpr int kPer = L::kGroups / 32;
-  uint32_t local = 0;
-  const uint32_t gBase = sGrp + lane * (uint32_t)kPer * 4u;
-#pragma unroll 4
-  for (int k = 0; k < kPer; k++)
-    local += __popc(lds_u32(gBase + k * 4u));
-  uint32_t scan = local;
+  // prefix of start counts over the groups, 32 groups per step (lane <-> group: conflict-free)
+  uint32_t carry = 0;
+#pragma unroll 2
+  for (uint32_t g0 = 0; g0 < (uint32_t)L::kGroups; g0 += 32u) {
+    const uint32_t a = sGrp + (g0 + lane) * 4u;
+    const uint32_t bm = lds_u32(a);
+    const uint32_t c = __popc(bm);
+    uint32_t scan = c;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t up = __shfl_up_sync(kFull, scan, d);
-    if (lane >= (uint32_t)d)
-      scan += up;
-  }
-  uint32_t before = scan - local;
-#pragma unroll 4
-  for (int k = 0; k < kPer; k++) {
-    const uint32_t bm = lds_u32(gBase + k * 4u);
-    sts_u32(gBase + k * 4u, ((before * 8u) << 16) | bm);
-    before += __popc(bm);
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(kFull, scan, d);
+      if (lane >= (uint32_t)d)
+        scan += up;
+    }
+    sts_u32(a, (((carry + scan - c) * 4u) << 16) | bm);
+    carry += __shfl_sync(kFull, scan, 31);
   }
   __syncwarp();
 
   if constexpr (TK == TK_PACKED) {
-    // expand to one u32 per slot: {freq:12 | slot - cumul:12 | symbol:8}
-    const uint32_t sPk = smem_u32(smemWarp + L::kOffPacked);
+    // expand to one u32 per slot: {freq:12 | symbol:8 | slot - cumul:12}
+    const uint32_t sPk = smemWarp + L::kOffPacked;
     for (uint32_t slot = lane; slot < (uint32_t)L::kSlots; slot += 32u) {
-      const uint32_t e = lds_u32(sGrp + ((slot >> 4) << 2));
-      const uint32_t cnt = __popc(e << (31u - (slot & 15u)));
-      const uint2 en = lds_u64(sEnt + (e >> 16) + cnt * 8u);
-      const uint32_t f = en.x + (uint32_t)L::kSlots;
-      const uint32_t bias = slot + (uint32_t)((int32_t)en.y >> 8);
-      sts_u32(sPk + slot * 4u, (f << 20) | (bias << 8) | (en.y & 0xffu));
+      const uint32_t g = lds_u32(sGrp + ((slot >> 4) << 2));
+      const uint32_t r4 = (g >> 16) + 4u * __popc(g << (31u - (slot & 15u)));
+      const uint32_t e = lds_u32(sEnt + r4);
+      const uint32_t s = lds_u8(sSym + (r4 >> 2));
+      const uint32_t f = (uint32_t)L::kSlots + (uint32_t)(int32_t)(int16_t)(e & 0xffffu);
+      const uint32_t bias = (slot + (uint32_t)((int32_t)e >> 16)) & 0xfffu;
+      sts_u32(sPk + slot * 4u, (f << 20) | (s << 12) | bias);
     }
     __syncwarp();
   }
-  return true;
-}
-
-// true if some symbol owns the whole range (freq == 2^BITS): the packed 12-bit field cannot hold it
-// (same limit as the reference's packed table, src/hist.cpp:304); callers route such tables to TK_RANK math.
-template <int BITS, int N, int TK>
-__device__ __forceinline__ bool table_is_degenerate(const uint8_t *smemWarp)
-{
-  using L = WarpLayout<BITS, N, TK>;
-  const uint2 en = lds_u64(smem_u32(smemWarp + L::kOffEnt) + 8u);
-  return en.x == 0u; // first present symbol has freq - 2^b == 0
+  return info;
 }
 
 // ---------------------------------------------------------------------------------------------- decode
@@ -274,97 +290,115 @@ template <int BITS, int N, int TK>
 struct Decoder {
   using L = WarpLayout<BITS, N, TK>;
 
-  uint32_t sGrp, sEnt, sPk;
-  bool degenerate; // warp-uniform: packed lookups would be wrong, use the rank table
+  uint32_t sGrp, sEnt, sSym, sPk; // shared addresses, compile-time constants after inlining
 
-  __device__ __forceinline__ void init(uint8_t *smemWarp)
+  __device__ __forceinline__ void init(uint32_t smemWarp)
   {
-    sGrp = smem_u32(smemWarp + L::kOffGrp);
-    sEnt = smem_u32(smemWarp + L::kOffEnt);
-    sPk = smem_u32(smemWarp + L::kOffPacked);
-    degenerate = false;
+    sGrp = smemWarp + L::kOffGrp;
+    sEnt = smemWarp + L::kOffEnt;
+    sSym = smemWarp + L::kOffSym;
+    sPk = smemWarp + L::kOffPacked;
   }
 
-  // symbol lookup + state update for one state; returns the symbol in the low byte
+  // symbol lookup + state update for one state; returns the symbol (low byte significant)
+  template <bool kAllPresent>
   __device__ __forceinline__ uint32_t symbol_step_rank(uint32_t &x) const
   {
-    const uint32_t e = lds_u32(sGrp + ((x >> 2) & (uint32_t)((L::kGroups - 1) << 2)));
-    const uint32_t cnt = __popc(e << ((~x & 15u) | 16u)); // starts at or below the slot, inside its group
-    const uint2 en = lds_u64(sEnt + (e >> 16) + cnt * 8u);
-    x = (x >> BITS) * en.x + x;                           // (x >> b) * freq + slot, since en.x = freq - 2^b
-    x += (uint32_t)((int32_t)en.y >> 8);                  // - cumul
-    return en.y;
+    const uint32_t g = lds_u32(sGrp + ((x >> 2) & (uint32_t)((L::kGroups - 1) << 2)));
+    uint32_t sh; // 31 - (x & 15) = (~x & 15) | 16 as ONE lop3 (immLut 0xAE = (~a & b) | c)
+    asm("lop3.b32 %0, %1, 15, 16, 0xAE;" : "=r"(sh) : "r"(x));
+    const uint32_t cnt = __popc(g << sh);      // starts at or below the slot inside its group
+    const uint32_t r4 = (g >> 16) + 4u * cnt;  // 4 * rank of the owning symbol
+    const uint32_t e = lds_u32(sEnt + r4);
+    x = (x >> BITS) * (uint32_t)(int32_t)(int16_t)(e & 0xffffu) + x; // (x >> b) * freq + slot
+    x += (uint32_t)((int32_t)e >> 16);                               // - cumul
+    if constexpr (kAllPresent)
+      return r4 >> 2;
+    else
+      return lds_u8(sSym + (r4 >> 2));
   }
 
   __device__ __forceinline__ uint32_t symbol_step_packed(uint32_t &x) const
   {
     const uint32_t e = lds_u32(sPk + ((x & (uint32_t)(L::kSlots - 1)) << 2));
-    x = (x >> BITS) * (e >> 20) + ((e >> 8) & 0xfffu);
-    return e;
+    x = (x >> BITS) * (e >> 20) + (e & 0xfffu);
+    return e >> 12;
   }
 
-  __device__ __forceinline__ uint32_t symbol_step(uint32_t &x) const
+  // Renormalise one full half-row; `wp` is the shared address of the warp cursor in the word ring. Written in
+  // PTX so that exactly one predicate feeds the ballot, the word load and the merge:
+  //   p = x < 2^15; m = ballot(p); w = words[wp + 2 * popc(m & lanemask_lt)]; if (p) x = x << 16 | w; wp += 2 * popc(m)
+  __device__ __forceinline__ void renorm(uint32_t &x, uint32_t &wp, uint32_t ltMask) const
   {
-    if constexpr (TK == TK_PACKED)
-      return symbol_step_packed(x);
-    else
-      return symbol_step_rank(x);
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 ".reg .u32 m, r, w, c;\n\t"
+                 "setp.lt.u32 p, %0, 32768;\n\t"
+                 "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+                 "and.b32 r, m, %2;\n\t"
+                 "popc.b32 r, r;\n\t"
+                 "mad.lo.u32 r, r, 2, %1;\n\t"
+                 "ld.shared.u16 w, [r];\n\t"
+                 "@p prmt.b32 %0, w, %0, 0x5410;\n\t"
+                 "popc.b32 c, m;\n\t"
+                 "mad.lo.u32 %1, c, 2, %1;\n\t"
+                 "}"
+                 : "+r"(x), "+r"(wp)
+                 : "r"(ltMask)
+                 : "memory");
   }
 
-  // renormalise the states of one half-row; `wordAddr` is the shared address of the warp cursor
-  __device__ __forceinline__ void renorm(uint32_t &x, uint32_t &wordAddr, uint32_t &cur, bool active, uint32_t ltMask) const
+  // the same for the ragged last row: only `active` lanes hold a symbol
+  __device__ __forceinline__ void renorm_masked(uint32_t &x, uint32_t &wp, bool active, uint32_t ltMask) const
   {
     const bool need = active && x < kConsumePoint16;
     const uint32_t m = __ballot_sync(kFull, need);
-    if (need) {
-      const uint32_t w = lds_u16(wordAddr + 2u * __popc(m & ltMask));
-      x = (x << 16) | w;
-    }
-    const uint32_t adv = 2u * __popc(m);
-    wordAddr += adv;
-    cur += adv;
+    const uint32_t w = lds_u16(wp + 2u * __popc(m & ltMask));
+    x = need ? ((x << 16) | w) : x;
+    wp += 2u * __popc(m);
   }
 
-  // full rows: `rows` rows of N symbols starting at out (already offset by the lane's byte position)
-  template <bool kDegenerate>
-  __device__ __forceinline__ void rows_impl(uint32_t &x0, uint32_t &x1, WordRing<L> &ring, uint8_t *outLane, uint64_t rows,
+  // mode 0: packed table, 1: rank table with all symbols present, 2: rank table with the rank->symbol map
+  template <int kMode>
+  __device__ __forceinline__ void rows_impl(uint32_t &x0, uint32_t &x1, WordRing<L> &ring, uint8_t *outLane, uint32_t rows,
                                             uint32_t lane, uint32_t ltMask) const
   {
-    for (uint64_t r = 0; r < rows; r++) {
+    for (uint32_t r = 0; r < rows; r++) {
       ring.advance_if_needed(lane);
-      uint32_t wa = ring.cursor_addr();
-      uint32_t cur = ring.cur;
       uint32_t s0, s1 = 0;
-      if constexpr (kDegenerate || TK == TK_RANK) {
-        s0 = symbol_step_rank(x0);
-        if constexpr (N == 64)
-          s1 = symbol_step_rank(x1);
-      } else {
+      if constexpr (kMode == 0) {
         s0 = symbol_step_packed(x0);
         if constexpr (N == 64)
           s1 = symbol_step_packed(x1);
+      } else {
+        s0 = symbol_step_rank<kMode == 1>(x0);
+        if constexpr (N == 64)
+          s1 = symbol_step_rank<kMode == 1>(x1);
       }
       st_global_u8(outLane, s0);
-      renorm(x0, wa, cur, true, ltMask);
+      renorm(x0, ring.wp, ltMask);
       if constexpr (N == 64) {
         st_global_u8(outLane + 32, s1);
-        renorm(x1, wa, cur, true, ltMask);
+        renorm(x1, ring.wp, ltMask);
       }
-      ring.cur = cur;
       outLane += N;
     }
   }
 
-  __device__ __forceinline__ void rows(uint32_t &x0, uint32_t &x1, WordRing<L> &ring, uint8_t *outLane, uint64_t nrows,
-                                       uint32_t lane, uint32_t ltMask) const
+  __device__ __forceinline__ void rows(const TableInfo &info, uint32_t &x0, uint32_t &x1, WordRing<L> &ring, uint8_t *outLane,
+                                       uint64_t nrows, uint32_t lane, uint32_t ltMask) const
   {
-    if constexpr (TK == TK_PACKED) {
-      if (degenerate) {
-        rows_impl<true>(x0, x1, ring, outLane, nrows, lane, ltMask);
-        return;
-      }
+    while (nrows) { // 64-bit row counts are split so the hot loop keeps a 32-bit counter
+      const uint32_t chunk = nrows > 0x40000000ull ? 0x40000000u : (uint32_t)nrows;
+      if (TK == TK_PACKED && !info.degenerate)
+        rows_impl<0>(x0, x1, ring, outLane, chunk, lane, ltMask);
+      else if (info.allPresent)
+        rows_impl<1>(x0, x1, ring, outLane, chunk, lane, ltMask);
+      else
+        rows_impl<2>(x0, x1, ring, outLane, chunk, lane, ltMask);
+      outLane += (uint64_t)chunk * N;
+      nrows -= chunk;
     }
-    rows_impl<false>(x0, x1, ring, outLane, nrows, lane, ltMask);
   }
 
   // the < N leftover symbols (src/rANS32x32_16w.cpp:238-266): lanes whose byte position is inside the buffer
@@ -372,27 +406,24 @@ struct Decoder {
                                        uint32_t left, uint32_t lane, uint32_t ltMask) const
   {
     ring.advance_if_needed(lane);
-    uint32_t wa = ring.cursor_addr();
-    uint32_t cur = ring.cur;
     const bool a0 = lanePos < left;
     uint32_t t0 = x0;
-    const uint32_t s0 = symbol_step_rank(t0); // the rank table is always built
+    const uint32_t s0 = symbol_step_rank<false>(t0); // the rank table is always built
     if (a0) {
       x0 = t0;
       st_global_u8(outLane, s0);
     }
-    renorm(x0, wa, cur, a0, ltMask);
+    renorm_masked(x0, ring.wp, a0, ltMask);
     if constexpr (N == 64) {
       const bool a1 = lanePos + 32u < left;
       uint32_t t1 = x1;
-      const uint32_t s1 = symbol_step_rank(t1);
+      const uint32_t s1 = symbol_step_rank<false>(t1);
       if (a1) {
         x1 = t1;
         st_global_u8(outLane + 32, s1);
       }
-      renorm(x1, wa, cur, a1, ltMask);
+      renorm_masked(x1, ring.wp, a1, ltMask);
     }
-    ring.cur = cur;
   }
 };
 

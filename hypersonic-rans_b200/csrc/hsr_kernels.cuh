@@ -33,16 +33,14 @@ __device__ __forceinline__ void raise(uint32_t *counter, uint32_t bits, uint32_t
 
 // ---------------------------------------------------------------------------------------------- mt_ / raw
 
-// Persistent warps pull units (mt_ blocks, fills, or one raw stream) from a global counter. Each warp owns a
-// private slice of shared memory: tables for its current block + its word ring.
-template <int BITS, int N, int TK, int WARPS>
+// Persistent one-warp CTAs pull units (mt_ blocks, fills, or one raw stream) from a global counter. The CTA's
+// static shared memory holds the tables of its current block + its word ring at compile-time addresses.
+template <int BITS, int N, int TK>
 __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
 {
   using L = WarpLayout<BITS, N, TK>;
-  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t sw = declare_smem<L::kBytes>();
   const uint32_t lane = lane_id();
-  const uint32_t warp = threadIdx.x >> 5;
-  uint8_t *sw = smem + warp * L::kBytes;
   const uint32_t ltMask = lanemask_lt();
   const uint32_t lanePos = idx2idx_lane(lane);
 
@@ -77,12 +75,11 @@ __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
     const uint8_t *countsPtr = kind == 0u ? base + 4 * N : base;
     const uint8_t *words = base + 4 * N + 512;
 
-    if (!build_tables<BITS, N, TK>(sw, countsPtr, lane)) {
+    const TableInfo info = build_tables<BITS, N, TK>(sw, countsPtr, lane);
+    if (!info.ok) {
       raise(p.counter, HSR_ERR_HIST, lane);
       continue;
     }
-    if constexpr (TK == TK_PACKED)
-      dec.degenerate = table_is_degenerate<BITS, N, TK>(sw);
 
     uint32_t x0 = ldg_u32_a2(statesPtr + 4 * lane);
     uint32_t x1 = 0;
@@ -90,15 +87,15 @@ __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
       x1 = ldg_u32_a2(statesPtr + 4 * (lane + 32));
 
     WordRing<L> ring;
-    ring.start(smem_u32(sw + L::kOffRing), words, end, lane);
+    ring.start(sw + L::kOffRing, words, end, lane);
 
     const uint64_t rows = (count - tailCount) / N;
     uint8_t *outLane = out + lanePos;
-    dec.rows(x0, x1, ring, outLane, rows, lane, ltMask);
+    dec.rows(info, x0, x1, ring, outLane, rows, lane, ltMask);
     if (tailCount)
       dec.tail(x0, x1, ring, outLane + rows * N, lanePos, tailCount, lane, ltMask);
     ring.drain();
-    if (ring.cur > ring.glimit)
+    if (ring.cursor() > ring.glimit)
       raise(p.counter, HSR_ERR_OVERRUN, lane);
   }
 }
@@ -112,14 +109,14 @@ template <int BITS, int N, int TK>
 __device__ __forceinline__ void block_kernel_body(const BlockStreamParams &p)
 {
   using L = WarpLayout<BITS, N, TK>;
-  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t sw = declare_smem<L::kBytes>();
   const uint32_t lane = lane_id();
-  uint8_t *sw = smem;
   const uint32_t ltMask = lanemask_lt();
   const uint32_t lanePos = idx2idx_lane(lane);
 
   Decoder<BITS, N, TK> dec;
   dec.init(sw);
+  TableInfo info{false, false, false};
 
   const uint8_t *in = p.in;
   const uint8_t *streamEnd = p.in + p.inLength;
@@ -135,7 +132,7 @@ __device__ __forceinline__ void block_kernel_body(const BlockStreamParams &p)
   uint64_t i = 0;
   bool haveHist = false;
   WordRing<L> ring;
-  const uint32_t sRing = smem_u32(sw + L::kOffRing);
+  const uint32_t sRing = sw + L::kOffRing;
 
   do {
     if (pos + 8 > p.inLength) {
@@ -158,12 +155,11 @@ __device__ __forceinline__ void block_kernel_body(const BlockStreamParams &p)
         raise(p.counter, HSR_ERR_OVERRUN, lane);
         return;
       }
-      if (!build_tables<BITS, N, TK>(sw, in + pos, lane)) { // :69-76
+      info = build_tables<BITS, N, TK>(sw, in + pos, lane); // :69-76
+      if (!info.ok) {
         raise(p.counter, HSR_ERR_HIST, lane);
         return;
       }
-      if constexpr (TK == TK_PACKED)
-        dec.degenerate = table_is_degenerate<BITS, N, TK>(sw);
       haveHist = true;
       pos += 512;
 
@@ -176,13 +172,13 @@ __device__ __forceinline__ void block_kernel_body(const BlockStreamParams &p)
       }
       const uint64_t rows = blockEnd > i ? (blockEnd - i + N - 1) / N : 0;
       ring.start(sRing, in + pos, streamEnd, lane);
-      dec.rows(x0, x1, ring, p.out + i + lanePos, rows, lane, ltMask);
+      dec.rows(info, x0, x1, ring, p.out + i + lanePos, rows, lane, ltMask);
       ring.drain();
-      if (ring.cur > ring.glimit) {
+      if (ring.cursor() > ring.glimit) {
         raise(p.counter, HSR_ERR_OVERRUN, lane);
         return;
       }
-      pos = (uint64_t)(ring.gbase - in) + ring.cur;
+      pos = (uint64_t)(ring.gbase - in) + ring.cursor();
       i += rows * N;
     }
     if (i > outLengthInStates) { // :88-94
@@ -209,10 +205,9 @@ typedef void (*units_kernel_t)(DecodeParams);
 typedef void (*block_kernel_t)(BlockStreamParams);
 
 struct KernelEntry {
-  const void *unitsW4; // 4 warps per CTA (mt_)
-  const void *unitsW1; // 1 warp per CTA (raw: one stream)
-  const void *block;   // block_ framing, 1 warp
-  int warpBytes;       // shared memory per warp
+  const void *units; // mt_ blocks / fills / one raw stream; one warp per CTA, persistent
+  const void *block; // block_ framing, one warp
+  int smemBytes;     // static shared memory per CTA
 };
 
 // defined in hsr_kernels_n32.cu / hsr_kernels_n64.cu; index [bits - 10][table - 1]

@@ -6,23 +6,19 @@ namespace hsr {
 
 #define HSR_CAT2(a, b) a##b
 #define HSR_CAT(a, b) HSR_CAT2(a, b)
-// e.g. units_w4_n64_b15_t1: mt_/raw units kernel, 4 warps per CTA, 64 states, 15 bits, table kind 1 (bitmap-rank)
+// e.g. units_n64_b15_t1: mt_/raw units kernel, 64 states, 15 bits, table kind 1 (bitmap-rank)
 #define HSR_NAME(prefix, BITS, TK) HSR_CAT(prefix, HSR_CAT(HSR_N, HSR_CAT(_b, HSR_CAT(BITS, HSR_CAT(_t, TK)))))
 
-// 48 registers keeps 40 warps per SM resident; the decode loop needs ~40.
+// 64 registers keep 32 one-warp CTAs per SM resident (the hardware limit); the decode loop needs ~50.
 #define HSR_DEFINE(BITS, TK)                                                                                          \
-  __global__ void __launch_bounds__(128, 8) HSR_NAME(units_w4_n, BITS, TK)(DecodeParams p)         \
-  { units_kernel_body<BITS, HSR_N, TK, 4>(p); }                                                                       \
-  __global__ void __launch_bounds__(32, 1) HSR_NAME(units_w1_n, BITS, TK)(DecodeParams p)          \
-  { units_kernel_body<BITS, HSR_N, TK, 1>(p); }                                                                       \
-  __global__ void __launch_bounds__(32, 1) HSR_NAME(block_w1_n, BITS, TK)(BlockStreamParams p)     \
+  __global__ void __launch_bounds__(32, 32) HSR_NAME(units_n, BITS, TK)(DecodeParams p)                               \
+  { units_kernel_body<BITS, HSR_N, TK>(p); }                                                                          \
+  __global__ void __launch_bounds__(32, 1) HSR_NAME(block_n, BITS, TK)(BlockStreamParams p)                           \
   { block_kernel_body<BITS, HSR_N, TK>(p); }
 
 #define HSR_ENTRY(BITS, TK)                                                                                           \
-  { (const void *)HSR_NAME(units_w4_n, BITS, TK),                                                  \
-    (const void *)HSR_NAME(units_w1_n, BITS, TK),                                                  \
-    (const void *)HSR_NAME(block_w1_n, BITS, TK), WarpLayout<BITS, HSR_N, TK>::kBytes }
-#define HSR_NONE { nullptr, nullptr, nullptr, 0 }
+  { (const void *)HSR_NAME(units_n, BITS, TK), (const void *)HSR_NAME(block_n, BITS, TK), WarpLayout<BITS, HSR_N, TK>::kBytes }
+#define HSR_NONE { nullptr, nullptr, 0 }
 
 HSR_DEFINE(10, 1) HSR_DEFINE(11, 1) HSR_DEFINE(12, 1) HSR_DEFINE(13, 1) HSR_DEFINE(14, 1) HSR_DEFINE(15, 1)
 HSR_DEFINE(10, 2) HSR_DEFINE(11, 2) HSR_DEFINE(12, 2)
