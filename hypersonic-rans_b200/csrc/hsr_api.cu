@@ -575,6 +575,7 @@ struct DeviceCtx {
   uint8_t *dIn = nullptr; size_t inCap = 0;
   uint8_t *dOut = nullptr; size_t outCap = 0;
   hsr_block_t *dBlocks = nullptr; size_t blocksCap = 0;
+  hsr_block_t *hBlocks = nullptr; size_t hBlocksCap = 0; // pinned + mapped: kernels read the index straight from host memory
   uint32_t *dCounters = nullptr; size_t countersCap = 0; // 4 u32 per chunk: counter, status, pad, pad
   std::vector<cudaEvent_t> evIn, evRun;
 };
@@ -610,6 +611,20 @@ static bool grow(T *&p, size_t &cap, size_t need)
   return true;
 }
 
+// The block index of a host-pointer decode lives in pinned, device-mapped host memory. A separate H2D copy of it
+// would queue on the copy-in engine BEHIND the stream pieces already in flight and hold back the first kernel
+// until the whole stream has landed; 48 bytes per block over PCIe are nothing next to a block's decode time.
+static bool grow_host_blocks(DeviceCtx *c, size_t need)
+{
+  if (need <= c->hBlocksCap) return true;
+  if (c->hBlocks) cudaFreeHost(c->hBlocks);
+  c->hBlocks = nullptr; c->hBlocksCap = 0;
+  const size_t want = need + need / 4 + 1024;
+  CU_TRY(cudaHostAlloc(&c->hBlocks, want * sizeof(hsr_block_t), cudaHostAllocMapped | cudaHostAllocPortable), return false);
+  c->hBlocksCap = want;
+  return true;
+}
+
 static bool ensure_events(DeviceCtx *c, size_t nChunks)
 {
   while (c->evIn.size() < nChunks) {
@@ -621,8 +636,94 @@ static bool ensure_events(DeviceCtx *c, size_t nChunks)
   return true;
 }
 
-// Decodes units [first, last) of an mt_ stream (or the single raw unit) held in host memory on `device`:
-// chunked H2D -> decode -> D2H with the three stages overlapped on three streams.
+// Host -> device copy of stream bytes [lo, hi) in fixed-size pieces on the copy-in stream; piece k covers bytes up
+// to ends[k] and signals evIn[k]. Issued before the block index exists, so the header walk overlaps the DMA.
+struct InFlight {
+  uint64_t lo = 0;
+  std::vector<uint64_t> ends;
+};
+
+static bool start_h2d(DeviceCtx *c, const uint8_t *in, uint64_t lo, uint64_t hi, InFlight *fl)
+{
+  const long optMb = g_optChunkMb;
+  const uint64_t piece = (optMb > 0 ? (uint64_t)optMb : 16ull) << 20;
+  fl->lo = lo;
+  fl->ends.clear();
+  if (!grow(c->dIn, c->inCap, (size_t)(hi - lo) + 16)) return false;
+  const size_t pieces = (size_t)((hi - lo + piece - 1) / piece);
+  if (!ensure_events(c, pieces)) return false;
+  for (size_t k = 0; k < pieces; k++) {
+    const uint64_t a = lo + k * piece, b = std::min(hi, a + piece);
+    CU_TRY(cudaMemcpyAsync(c->dIn + (a - lo), in + a, (size_t)(b - a), cudaMemcpyHostToDevice, c->sIn), return false);
+    CU_TRY(cudaEventRecord(c->evIn[k], c->sIn), return false);
+    fl->ends.push_back(b);
+  }
+  return true;
+}
+
+// Decodes units [first, last) whose compressed bytes are arriving through `fl`: contiguous unit ranges are
+// launched as soon as the copy piece holding their last byte has landed, and each range's decoded bytes go back
+// to the host while later ranges are still decoding (three streams: copy-in, run, copy-out).
+static bool run_units_pipelined(DeviceCtx *c, int N, int bits, uint8_t *out, const hsr_block_t *units, size_t first, size_t last,
+                                const InFlight &fl)
+{
+  if (first >= last) return true;
+  const uint64_t outLo = units[first].outOffset, outHi = units[last - 1].outOffset + units[last - 1].count;
+  const size_t count = last - first;
+
+  const uint64_t rangeBytes = 48ull << 20; // compressed + decoded traffic per launch
+  std::vector<size_t> cuts{first};
+  uint64_t acc = 0;
+  for (size_t k = first; k < last; k++) {
+    acc += (units[k].inEnd - units[k].inOffset) + units[k].count;
+    if (acc >= rangeBytes && k + 1 < last) { cuts.push_back(k + 1); acc = 0; }
+  }
+  cuts.push_back(last);
+  const size_t nRanges = cuts.size() - 1;
+
+  if (!grow(c->dOut, c->outCap, (size_t)(outHi - outLo) + 16)) return false;
+  if (!grow(c->dCounters, c->countersCap, nRanges * 4)) return false;
+  const hsr_block_t *devBlocks = nullptr; // device-visible address of units[first]
+  if (units >= c->hBlocks && units + last <= c->hBlocks + c->hBlocksCap) {
+    devBlocks = units + first; // already in the mapped buffer (UVA: same address on the device)
+  } else {
+    if (!grow_host_blocks(c, count)) return false;
+    memcpy(c->hBlocks, units + first, count * sizeof(hsr_block_t));
+    devBlocks = c->hBlocks;
+  }
+  while (c->evRun.size() < nRanges) {
+    cudaEvent_t e;
+    CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), return false);
+    c->evRun.push_back(e);
+  }
+
+  CU_TRY(cudaMemsetAsync(c->dCounters, 0, nRanges * 16, c->sRun), return false);
+
+  size_t piece = 0;
+  for (size_t r = 0; r < nRanges; r++) {
+    const size_t a = cuts[r], b = cuts[r + 1];
+    const uint64_t needEnd = units[b - 1].inEnd;
+    while (piece + 1 < fl.ends.size() && fl.ends[piece] < needEnd) piece++;
+    CU_TRY(cudaStreamWaitEvent(c->sRun, c->evIn[piece], 0), return false);
+    if (launch_units(N, bits, c->dIn, fl.lo, c->dOut, outLo, devBlocks + (a - first), (uint32_t)(b - a), c->dCounters + 4 * r, c->sRun) < 0)
+      return false;
+    CU_TRY(cudaEventRecord(c->evRun[r], c->sRun), return false);
+    CU_TRY(cudaStreamWaitEvent(c->sOut, c->evRun[r], 0), return false);
+    const uint64_t oLo = units[a].outOffset, oHi = units[b - 1].outOffset + units[b - 1].count;
+    CU_TRY(cudaMemcpyAsync(out + oLo, c->dOut + (oLo - outLo), (size_t)(oHi - oLo), cudaMemcpyDeviceToHost, c->sOut), return false);
+  }
+  std::vector<uint32_t> status(nRanges * 4);
+  CU_TRY(cudaMemcpyAsync(status.data(), c->dCounters, nRanges * 16, cudaMemcpyDeviceToHost, c->sOut), return false);
+  CU_TRY(cudaStreamSynchronize(c->sOut), return false);
+  CU_TRY(cudaStreamSynchronize(c->sIn), return false);
+  CU_TRY(cudaStreamSynchronize(c->sRun), return false);
+  uint32_t bad = 0;
+  for (size_t r = 0; r < nRanges; r++) bad |= status[4 * r + 1];
+  if (bad) { set_err("malformed stream (device status 0x%x)", bad); return false; }
+  return true;
+}
+
+// units [first, last) of an already indexed stream, from host memory, on `device`
 static bool decode_units_from_host(int device, int N, int bits, const uint8_t *in, uint8_t *out, const hsr_block_t *units,
                                    size_t first, size_t last)
 {
@@ -631,55 +732,9 @@ static bool decode_units_from_host(int device, int N, int bits, const uint8_t *i
   DeviceCtx *c = get_ctx(device);
   if (!c) return false;
   std::lock_guard<std::mutex> lock(c->mu);
-
-  const uint64_t inLo = units[first].inOffset & ~15ull, inHi = units[last - 1].inEnd;
-  const uint64_t outLo = units[first].outOffset, outHi = units[last - 1].outOffset + units[last - 1].count;
-  const size_t count = last - first;
-
-  // chunk boundaries: contiguous unit ranges of about chunkBytes of compressed + decoded traffic
-  const long optMb = g_optChunkMb;
-  const uint64_t chunkBytes = (optMb > 0 ? (uint64_t)optMb : 32ull) << 20;
-  std::vector<size_t> cuts{first};
-  uint64_t acc = 0;
-  for (size_t k = first; k < last; k++) {
-    acc += (units[k].inEnd - units[k].inOffset) + units[k].count;
-    if (acc >= chunkBytes && k + 1 < last) { cuts.push_back(k + 1); acc = 0; }
-  }
-  cuts.push_back(last);
-  const size_t nChunks = cuts.size() - 1;
-
-  if (!grow(c->dIn, c->inCap, (size_t)(inHi - inLo) + 16)) return false;
-  if (!grow(c->dOut, c->outCap, (size_t)(outHi - outLo) + 16)) return false;
-  if (!grow(c->dBlocks, c->blocksCap, count)) return false;
-  if (!grow(c->dCounters, c->countersCap, nChunks * 4)) return false;
-  if (!ensure_events(c, nChunks)) return false;
-
-  CU_TRY(cudaMemcpyAsync(c->dBlocks, units + first, count * sizeof(hsr_block_t), cudaMemcpyHostToDevice, c->sRun), return false);
-  CU_TRY(cudaMemsetAsync(c->dCounters, 0, nChunks * 16, c->sRun), return false);
-
-  for (size_t ch = 0; ch < nChunks; ch++) {
-    const size_t a = cuts[ch], b = cuts[ch + 1];
-    const uint64_t cLo = ch == 0 ? inLo : units[a].inOffset & ~15ull; // re-sending < 16 bytes keeps copies aligned
-    const uint64_t cHi = units[b - 1].inEnd;
-    CU_TRY(cudaMemcpyAsync(c->dIn + (cLo - inLo), in + cLo, (size_t)(cHi - cLo), cudaMemcpyHostToDevice, c->sIn), return false);
-    CU_TRY(cudaEventRecord(c->evIn[ch], c->sIn), return false);
-    CU_TRY(cudaStreamWaitEvent(c->sRun, c->evIn[ch], 0), return false);
-    if (launch_units(N, bits, c->dIn, inLo, c->dOut, outLo, c->dBlocks + (a - first), (uint32_t)(b - a), c->dCounters + 4 * ch, c->sRun) < 0)
-      return false;
-    CU_TRY(cudaEventRecord(c->evRun[ch], c->sRun), return false);
-    CU_TRY(cudaStreamWaitEvent(c->sOut, c->evRun[ch], 0), return false);
-    const uint64_t oLo = units[a].outOffset, oHi = units[b - 1].outOffset + units[b - 1].count;
-    CU_TRY(cudaMemcpyAsync(out + oLo, c->dOut + (oLo - outLo), (size_t)(oHi - oLo), cudaMemcpyDeviceToHost, c->sOut), return false);
-  }
-  std::vector<uint32_t> status(nChunks * 4);
-  CU_TRY(cudaMemcpyAsync(status.data(), c->dCounters, nChunks * 16, cudaMemcpyDeviceToHost, c->sOut), return false);
-  CU_TRY(cudaStreamSynchronize(c->sOut), return false);
-  CU_TRY(cudaStreamSynchronize(c->sIn), return false);
-  CU_TRY(cudaStreamSynchronize(c->sRun), return false);
-  uint32_t bad = 0;
-  for (size_t ch = 0; ch < nChunks; ch++) bad |= status[4 * ch + 1];
-  if (bad) { set_err("malformed stream (device status 0x%x)", bad); return false; }
-  return true;
+  InFlight fl;
+  if (!start_h2d(c, in, units[first].inOffset & ~15ull, units[last - 1].inEnd, &fl)) return false;
+  return run_units_pipelined(c, N, bits, out, units, first, last, fl);
 }
 
 static bool decode_block_from_host(int device, int N, int bits, const uint8_t *in, const Header &h, uint8_t *out)
@@ -720,11 +775,23 @@ extern "C" size_t hsr_decode(int family, int N, int bits, const uint8_t *in, siz
     const hsr_block_t u = raw_unit(N, h);
     return decode_units_from_host(device, N, bits, in, out, &u, 0, 1) ? (size_t)h.n : 0;
   }
-  const long cnt = hsr_mt_index(N, in, (size_t)h.compLen, nullptr, 0);
-  if (cnt < 0) return 0;
-  std::vector<hsr_block_t> units((size_t)cnt);
-  if (hsr_mt_index(N, in, (size_t)h.compLen, units.data(), units.size()) != cnt) return 0;
-  return decode_units_from_host(device, N, bits, in, out, units.data(), 0, units.size()) ? (size_t)h.n : 0;
+  // mt_: start moving the whole stream to the device, walk the header chain on the host meanwhile
+  DeviceCtx *c = get_ctx(device);
+  if (!c) return 0;
+  std::lock_guard<std::mutex> lock(c->mu);
+  InFlight fl;
+  if (!start_h2d(c, in, 0, h.compLen, &fl)) return 0;
+  if (!grow_host_blocks(c, (size_t)std::max<uint64_t>(64, h.n / 32768 + 64))) return 0;
+  long cnt = hsr_mt_index(N, in, (size_t)h.compLen, c->hBlocks, c->hBlocksCap);
+  if (cnt > (long)c->hBlocksCap) {
+    if (!grow_host_blocks(c, (size_t)cnt)) return 0;
+    cnt = hsr_mt_index(N, in, (size_t)h.compLen, c->hBlocks, c->hBlocksCap);
+  }
+  if (cnt < 0) {
+    cudaStreamSynchronize(c->sIn);
+    return 0;
+  }
+  return run_units_pipelined(c, N, bits, out, c->hBlocks, 0, (size_t)cnt, fl) ? (size_t)h.n : 0;
 }
 
 extern "C" size_t hsr_decode_mt_multi(int N, int bits, const uint8_t *in, size_t inLength, uint8_t *out, size_t outCapacity,

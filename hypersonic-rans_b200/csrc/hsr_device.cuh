@@ -12,7 +12,7 @@
 // One CTA = one warp, so every table lives at a compile-time shared-memory address and lookups are
 // LDS [reg + imm]. Shared-memory tables (private layouts; only the decoded bytes have to match the reference):
 //   TK_RANK   bitmap-rank table, any bits:
-//               grp[2^b / 16]  u32  {4 * (symbol starts before this group) : 16 | start bitmap of its 16 slots : 16}
+//               grp[2^b / 16]  u32  {symbol starts before this group : 16 | start bitmap of its 16 slots : 16}
 //               ent[256]       u32  per PRESENT symbol, in slot order {-cumul : 16 | 2^b - freq : 16}
 //               sym[256]       u8   rank -> symbol (skipped when all 256 symbols are present: rank == symbol)
 //             2^(b-2) + 1.25 KB (9.25 KB at 15 bits vs 33 KB for the reference's hist_dec2_t, src/hist.h:32-37)
@@ -100,7 +100,7 @@ struct WarpLayout {
 
   // word ring: kBufs linear segments of kSeg bytes; consecutive segments overlap by one worst-case row
   static constexpr int kSeg = 512;                  // one 16-byte cp.async per lane
-  static constexpr int kBufs = 4;
+  static constexpr int kBufs = 3;
   static constexpr int kOverlap = 2 * N;            // a row consumes at most N words
   static constexpr int kStride = kSeg - kOverlap;
   static constexpr int kRingBytes = kSeg * kBufs;
@@ -262,7 +262,7 @@ __device__ __forceinline__ TableInfo build_tables(uint32_t smemWarp, const uint8
       if (lane >= (uint32_t)d)
         scan += up;
     }
-    sts_u32(a, (((carry + scan - c) * 4u) << 16) | bm);
+    sts_u32(a, ((carry + scan - c) << 16) | bm);
     carry += __shfl_sync(kFull, scan, 31);
   }
   __syncwarp();
@@ -272,9 +272,9 @@ __device__ __forceinline__ TableInfo build_tables(uint32_t smemWarp, const uint8
     const uint32_t sPk = smemWarp + L::kOffPacked;
     for (uint32_t slot = lane; slot < (uint32_t)L::kSlots; slot += 32u) {
       const uint32_t g = lds_u32(sGrp + ((slot >> 4) << 2));
-      const uint32_t r4 = (g >> 16) + 4u * __popc(g << (31u - (slot & 15u)));
-      const uint32_t e = lds_u32(sEnt + r4);
-      const uint32_t s = lds_u8(sSym + (r4 >> 2));
+      const uint32_t rank = (g >> 16) + __popc(g << (31u - (slot & 15u)));
+      const uint32_t e = lds_u32(sEnt + rank * 4u);
+      const uint32_t s = lds_u8(sSym + rank);
       const uint32_t f = (uint32_t)L::kSlots + (uint32_t)(int32_t)(int16_t)(e & 0xffffu);
       const uint32_t bias = (slot + (uint32_t)((int32_t)e >> 16)) & 0xfffu;
       sts_u32(sPk + slot * 4u, (f << 20) | (s << 12) | bias);
@@ -307,15 +307,14 @@ struct Decoder {
     const uint32_t g = lds_u32(sGrp + ((x >> 2) & (uint32_t)((L::kGroups - 1) << 2)));
     uint32_t sh; // 31 - (x & 15) = (~x & 15) | 16 as ONE lop3 (immLut 0xAE = (~a & b) | c)
     asm("lop3.b32 %0, %1, 15, 16, 0xAE;" : "=r"(sh) : "r"(x));
-    const uint32_t cnt = __popc(g << sh);      // starts at or below the slot inside its group
-    const uint32_t r4 = (g >> 16) + 4u * cnt;  // 4 * rank of the owning symbol
-    const uint32_t e = lds_u32(sEnt + r4);
+    const uint32_t rank = (g >> 16) + __popc(g << sh); // symbol starts at or below the slot = rank of its owner
+    const uint32_t e = lds_u32(sEnt + rank * 4u);
     x = (x >> BITS) * (uint32_t)(int32_t)(int16_t)(e & 0xffffu) + x; // (x >> b) * freq + slot
     x += (uint32_t)((int32_t)e >> 16);                               // - cumul
     if constexpr (kAllPresent)
-      return r4 >> 2;
+      return rank;
     else
-      return lds_u8(sSym + (r4 >> 2));
+      return lds_u8(sSym + rank);
   }
 
   __device__ __forceinline__ uint32_t symbol_step_packed(uint32_t &x) const
@@ -339,7 +338,7 @@ struct Decoder {
                  "popc.b32 r, r;\n\t"
                  "mad.lo.u32 r, r, 2, %1;\n\t"
                  "ld.shared.u16 w, [r];\n\t"
-                 "@p prmt.b32 %0, w, %0, 0x5410;\n\t"
+                 "@p mad.lo.u32 %0, %0, 65536, w;\n\t"
                  "popc.b32 c, m;\n\t"
                  "mad.lo.u32 %1, c, 2, %1;\n\t"
                  "}"
