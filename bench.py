@@ -358,8 +358,8 @@ def main():
         kernel_ms = float(np.mean(step_ms))
         achieved = (comp + n) / (kernel_ms * 1e-3) / 1e9
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
-        if os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")  # from the committed `ncu --set full` capture
+        if os.path.exists(tpath) and a.size == 1_000_000_000 and a.bits == 15 and a.states == 64 and a.shape == "pw64k":
             try:
                 traffic = json.load(open(tpath)).get("bytes_per_launch")
             except Exception:
@@ -376,7 +376,7 @@ def main():
                        "parallelism": f"{world} x contiguous block range, no collective",
                        "table": "auto (bitmap-rank for bits>=13, packed slot table below)"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": traffic, "peak_source": peak_src, "kernel": f"units_w4_n{a.states}_b{a.bits}",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": f"units_n{a.states}_b{a.bits}_t{2 if (a.bits <= 12 and a.table != 1) else 1}",
                          "algorithmic_bytes_per_launch": comp + n, "kernel_ms": round(kernel_ms, 4),
                          "kernel_ms_min": round(float(np.min(step_ms)), 4)},
             "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": comp, "d2h_bytes_per_step": n,
