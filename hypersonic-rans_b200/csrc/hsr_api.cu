@@ -230,7 +230,9 @@ static int pick_table(int bits)
   const long opt = g_optTable;
   if (opt == 1) return TK_RANK;
   if (opt == 2) return bits <= 12 ? TK_PACKED : TK_RANK;
-  return bits <= 12 ? TK_PACKED : TK_RANK;
+  // measured on B200 (profiles/r1/sweep_1g_v5.jsonl): the packed slot table wins while it leaves >= 19 CTAs per
+  // SM resident (4 / 8 KB at 10 / 11 bits); at 12 bits its 16 KB cost more occupancy than the second lookup costs
+  return bits <= 11 ? TK_PACKED : TK_RANK;
 }
 
 static const KernelEntry &kernel_entry(int N, int bits, int table) { return (N == 32 ? kKernels32 : kKernels64)[bits - 10][table - 1]; }

@@ -1,0 +1,24 @@
+"""Small decode set for compute-sanitizer (memcheck / racecheck / initcheck): every family, both N, bits 10/12/15."""
+import sys
+import numpy as np
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import __graft_entry__ as g
+pkg = g.load_package()
+z = np.load("tests/golden/golden.npz")
+bad = 0
+for key in sorted(z.files):
+    if not key.startswith("stream/"):
+        continue
+    _, name, fam, states, bits = key.split("/")
+    if name not in ("multi", "runs", "tiny65", "small") or int(bits) not in (10, 12, 15):
+        continue
+    data = z[f"in/{name}"]
+    for table in (0, 1):
+        pkg.set_option("table", table)
+        n, out = pkg.decode(int(fam), int(states), int(bits), z[key], data.size)
+        ok = n == data.size and np.array_equal(out[:n], data)
+        bad += not ok
+        print(key, "table", table, "ok" if ok else "MISMATCH")
+cnt, cum = pkg.make_hist(z["in/multi"], 12)
+print("hist ok", np.array_equal(cnt, z["hist/multi/12"][0]))
+sys.exit(1 if bad else 0)
