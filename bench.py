@@ -232,6 +232,38 @@ def single_recurrence_extras(pkg, torch, a):
         res[label] = {"gpu_decoded_GBps": round(n / ms / 1e6, 4), "gpu_ms": round(ms, 3), "bit_exact": ok,
                       "cpu_avx2_1thread_GBps": round(n / cpu_s / 1e9, 4), "streams": 1, "warps": 1}
         ps.free()
+
+    # the same two codecs with many independent streams in one launch (hsr_stream_upload_batch): one warp per stream
+    k_streams, each = 2368, 400_000
+    data = pkg.synth_zipf(k_streams * each, 1.0, seed=43, segment_bytes=0)
+    for label, fam, states, bits in (("rANS32x64_16w_12_raw", 0, 64, 12), ("block_rANS32x32_16w_10", 1, 32, 10)):
+        parts, items, pos = [], [], 0
+        for k in range(k_streams):
+            stream = ck.ref_encode(fam, states, bits, data[k * each:(k + 1) * each])
+            pad = (-pos) % 16
+            parts.append(np.zeros(pad, np.uint8)); pos += pad
+            items.append((pos, stream.size, k * each, each))
+            parts.append(stream); pos += stream.size
+        in_base = np.concatenate(parts)
+        ps = pkg.PreparedStream.upload_batch(fam, states, bits, in_base, items)
+        total = k_streams * each
+        out2 = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        ps.decode_async(out2.data_ptr(), total, st)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ps.decode_async(out2.data_ptr(), total, st)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        ok = ps.status() == 0 and bool(np.array_equal(out2[:total].cpu().numpy(), data))
+        res[label + "_batch"] = {"gpu_decoded_GBps": round(total / ms / 1e6, 2), "gpu_ms": round(ms, 3), "bit_exact": ok,
+                                 "streams": k_streams, "bytes_per_stream": each, "compressed_bytes": int(in_base.size),
+                                 "algorithmic_GBps": round((total + in_base.size) / ms / 1e6, 1)}
+        ps.free()
+        del out2
     return res
 
 

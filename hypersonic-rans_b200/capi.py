@@ -42,10 +42,12 @@ SIGNATURES = {
     "hsr_decode_mt_multi": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                          C.POINTER(C.c_int), C.c_int]),
     "hsr_set_device": (C.c_int, [C.c_int]),
+    "hsr_decode_batch": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "hsr_mt_index": (C.c_long, [C.c_int, C.c_void_p, C.c_size_t, C.POINTER(Block), C.c_size_t]),
     "hsr_mt_partition": (C.c_int, [C.POINTER(Block), C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]),
     "hsr_stream_upload": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
     "hsr_stream_from_device": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "hsr_stream_upload_batch": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "hsr_stream_free": (None, [C.c_void_p]),
     "hsr_stream_decoded_length": (C.c_uint64, [C.c_void_p]),
     "hsr_stream_shard_out_offset": (C.c_uint64, [C.c_void_p]),
@@ -166,6 +168,21 @@ def decode_mt_multi(state_count: int, bits: int, data, out_capacity: int, device
     return n, out
 
 
+class BatchItem(C.Structure):
+    """hsr_batch_item_t"""
+    _fields_ = [("inOffset", C.c_uint64), ("inLength", C.c_uint64), ("outOffset", C.c_uint64), ("outCapacity", C.c_uint64)]
+
+
+def decode_batch(family: int, state_count: int, bits: int, in_base, out_base: np.ndarray, items):
+    """Many independent streams of one codec in one launch. `items` = [(inOffset, inLength, outOffset, outCapacity)].
+    Returns (number decoded, per-stream decoded lengths)."""
+    src = _as_u8(in_base)
+    arr = (BatchItem * max(len(items), 1))(*[BatchItem(*map(int, it)) for it in items])
+    lengths = np.zeros(max(len(items), 1), np.uint64)
+    ok = lib().hsr_decode_batch(family, state_count, bits, _ptr(src), _ptr(out_base), arr, len(items), _ptr(lengths))
+    return ok, lengths[: len(items)]
+
+
 def mt_index(state_count: int, data) -> list:
     """Host walk of the mt_ header chain -> list of Block records (raises on a malformed chain)."""
     src = _as_u8(data)
@@ -199,6 +216,12 @@ class PreparedStream:
     def upload(cls, family: int, state_count: int, bits: int, data, shard: int = 0, shards: int = 1) -> "PreparedStream":
         src = _as_u8(data)
         return cls(lib().hsr_stream_upload(family, state_count, bits, _ptr(src), src.size, shard, shards))
+
+    @classmethod
+    def upload_batch(cls, family: int, state_count: int, bits: int, in_base, items) -> "PreparedStream":
+        src = _as_u8(in_base)
+        arr = (BatchItem * max(len(items), 1))(*[BatchItem(*map(int, it)) for it in items])
+        return cls(lib().hsr_stream_upload_batch(family, state_count, bits, _ptr(src), arr, len(items)))
 
     @classmethod
     def from_device(cls, family: int, state_count: int, bits: int, device_ptr: int, length: int) -> "PreparedStream":

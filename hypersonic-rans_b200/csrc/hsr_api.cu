@@ -225,13 +225,16 @@ extern "C" int hsr_mt_partition(const hsr_block_t *blocks, size_t count, int par
 
 // ------------------------------------------------------------------------------------------------ kernel launch
 
-static int pick_table(int bits)
+static int pick_table(int bits, size_t units = (size_t)-1)
 {
   const long opt = g_optTable;
   if (opt == 1) return TK_RANK;
   if (opt == 2) return bits <= 12 ? TK_PACKED : TK_RANK;
   // measured on B200 (profiles/r1/sweep_1g_v5.jsonl): the packed slot table wins while it leaves >= 19 CTAs per
   // SM resident (4 / 8 KB at 10 / 11 bits); at 12 bits its 16 KB cost more occupancy than the second lookup costs
+  // ... unless there are too few units to fill the GPU anyway (a single raw / block_ stream is ONE warp): then
+  // only the row latency counts and one lookup on the chain beats two
+  if (bits == 12 && units < 148u * 8u) return TK_PACKED;
   return bits <= 11 ? TK_PACKED : TK_RANK;
 }
 
@@ -265,12 +268,13 @@ static bool prepare_kernel(const void *fn, LaunchInfo *li)
 
 // launches the units kernel over `numBlocks` records of a device-resident index
 static int launch_units(int N, int bits, const uint8_t *dIn, uint64_t inBase, uint8_t *dOut, uint64_t outBase,
-                        const hsr_block_t *dBlocks, uint32_t numBlocks, uint32_t *dCounter, cudaStream_t st)
+                        const hsr_block_t *dBlocks, uint32_t numBlocks, uint32_t *dCounter, cudaStream_t st,
+                        uint32_t *dStreamStatus = nullptr)
 {
   if (numBlocks == 0) return 0;
-  const int table = pick_table(bits);
+  const int table = pick_table(bits, numBlocks);
   const KernelEntry &ke = kernel_entry(N, bits, table);
-  DecodeParams p{dIn, inBase, dOut, outBase, dBlocks, numBlocks, dCounter};
+  DecodeParams p{dIn, inBase, dOut, outBase, dBlocks, numBlocks, dCounter, dStreamStatus};
   void *args[] = {&p};
   CU_TRY(cudaMemsetAsync(dCounter, 0, 4, st), return -1); // work counter only; status bits accumulate
   LaunchInfo li;
@@ -286,11 +290,28 @@ static int launch_units(int N, int bits, const uint8_t *dIn, uint64_t inBase, ui
 static int launch_block_stream(int N, int bits, const uint8_t *dIn, uint64_t inLength, uint8_t *dOut, uint64_t n,
                                uint32_t *dCounter, cudaStream_t st)
 {
-  const int table = pick_table(bits);
+  const int table = pick_table(bits, 1);
   const KernelEntry &ke = kernel_entry(N, bits, table);
-  BlockStreamParams p{dIn, inLength, dOut, n, dCounter};
+  BlockStreamParams p{dIn, dOut, nullptr, BlockStreamDesc{0, inLength, 0, n}, 1u, dCounter, nullptr};
   void *args[] = {&p};
   CU_TRY(cudaLaunchKernel(ke.block, dim3(1), dim3(32), args, 0, st), return -1);
+  return 1;
+}
+
+// many independent block_ streams, one warp each
+static int launch_block_batch(int N, int bits, const uint8_t *dIn, uint8_t *dOut, const BlockStreamDesc *dStreams, uint32_t count,
+                              uint32_t *dCounter, uint32_t *dStreamStatus, cudaStream_t st)
+{
+  if (count == 0) return 0;
+  const int table = pick_table(bits, count);
+  const KernelEntry &ke = kernel_entry(N, bits, table);
+  BlockStreamParams p{dIn, dOut, dStreams, BlockStreamDesc{0, 0, 0, 0}, count, dCounter, dStreamStatus};
+  void *args[] = {&p};
+  CU_TRY(cudaMemsetAsync(dCounter, 0, 4, st), return -1);
+  LaunchInfo li;
+  if (!prepare_kernel(ke.block, &li)) return -1;
+  const uint32_t grid = std::min<uint32_t>(count, (uint32_t)(li.ctasPerSm * li.smCount));
+  CU_TRY(cudaLaunchKernel(ke.block, dim3(grid), dim3(32), args, 0, st), return -1);
   return 1;
 }
 
@@ -375,6 +396,10 @@ struct hsr_stream {
   uint32_t *dCounter = nullptr;    // [0] work counter, [1] status
   uint64_t outOffset = 0, outBytes = 0;
   double indexMs = 0;
+  // batch of independent streams (hsr_stream_upload_batch): block_ descriptors + per-stream status
+  BlockStreamDesc *dDescs = nullptr;
+  uint32_t numDescs = 0;
+  bool batch = false;
 };
 
 static void stream_release(hsr_stream *s)
@@ -385,6 +410,7 @@ static void stream_release(hsr_stream *s)
   cudaSetDevice(s->device);
   if (s->ownsIn && s->dIn) cudaFree(s->dIn);
   if (s->dBlocks) cudaFree(s->dBlocks);
+  if (s->dDescs) cudaFree(s->dDescs);
   if (s->dCounter) cudaFree(s->dCounter);
   cudaSetDevice(prev);
   delete s;
@@ -413,6 +439,59 @@ static hsr_block_t raw_unit(int N, const Header &h)
   b.kind = 2;
   b.tail = (uint32_t)(h.n % (uint64_t)N);
   return b;
+}
+
+// Work list of a batch of independent streams (hsr_decode_batch / hsr_stream_upload_batch).
+struct BatchPlan {
+  std::vector<Header> hdr;
+  std::vector<char> good;
+  std::vector<hsr_block_t> units;      // raw / mt_: offsets relative to inBase / outBase
+  std::vector<BlockStreamDesc> descs;  // block_: offsets relative to inLo / outLo
+  std::vector<uint32_t> descStream;
+  uint64_t inLo = ~0ull, inHi = 0, outLo = ~0ull, outHi = 0;
+};
+
+static bool plan_batch(int family, int N, const uint8_t *inBase, const hsr_batch_item_t *items, size_t count, BatchPlan *bp)
+{
+  bp->hdr.assign(count, Header{0, 0});
+  bp->good.assign(count, 0);
+  size_t nGood = 0;
+  // per-stream header checks (src/rANS32x32_16w.cpp:164-180); bad streams get length 0 and are skipped
+  for (size_t i = 0; i < count; i++) {
+    const hsr_batch_item_t &it = items[i];
+    if (!read_header(N, inBase + it.inOffset, (size_t)it.inLength, (size_t)it.outCapacity, &bp->hdr[i])) continue;
+    if (bp->hdr[i].compLen < 16 + 4 * (uint64_t)N + 512 || bp->hdr[i].compLen > kMaxUnitIn) continue;
+    bp->good[i] = 1;
+    nGood++;
+    bp->inLo = std::min<uint64_t>(bp->inLo, it.inOffset & ~15ull);
+    bp->inHi = std::max<uint64_t>(bp->inHi, it.inOffset + bp->hdr[i].compLen);
+    bp->outLo = std::min<uint64_t>(bp->outLo, it.outOffset);
+    bp->outHi = std::max<uint64_t>(bp->outHi, it.outOffset + bp->hdr[i].n);
+  }
+  if (nGood == 0) { set_err("no well-formed stream in the batch"); return false; }
+  for (size_t i = 0; i < count; i++) {
+    if (!bp->good[i]) continue;
+    const hsr_batch_item_t &it = items[i];
+    if (family == HSR_RAW) {
+      hsr_block_t u = raw_unit(N, bp->hdr[i]);
+      u.inOffset += it.inOffset; u.inEnd += it.inOffset; u.outOffset += it.outOffset; u.reserved = (uint32_t)i;
+      bp->units.push_back(u);
+    } else if (family == HSR_MT) {
+      const long cnt = hsr_mt_index(N, inBase + it.inOffset, (size_t)bp->hdr[i].compLen, nullptr, 0);
+      if (cnt < 0) { bp->good[i] = 0; continue; }
+      const size_t at = bp->units.size();
+      bp->units.resize(at + (size_t)cnt);
+      hsr_mt_index(N, inBase + it.inOffset, (size_t)bp->hdr[i].compLen, bp->units.data() + at, (size_t)cnt);
+      for (size_t k = at; k < bp->units.size(); k++) {
+        bp->units[k].inOffset += it.inOffset; bp->units[k].inEnd += it.inOffset; bp->units[k].outOffset += it.outOffset;
+        bp->units[k].reserved = (uint32_t)i;
+      }
+    } else {
+      bp->descs.push_back(BlockStreamDesc{it.inOffset - bp->inLo, bp->hdr[i].compLen, it.outOffset - bp->outLo, bp->hdr[i].n});
+      bp->descStream.push_back((uint32_t)i);
+    }
+  }
+  return true;
 }
 
 extern "C" hsr_stream_t *hsr_stream_upload(int family, int N, int bits, const uint8_t *in, size_t inLength, int shard, int shards)
@@ -527,11 +606,45 @@ extern "C" hsr_stream_t *hsr_stream_from_device(int family, int N, int bits, con
   return s.release();
 }
 
+extern "C" hsr_stream_t *hsr_stream_upload_batch(int family, int N, int bits, const uint8_t *inBase, const hsr_batch_item_t *items,
+                                                 size_t count)
+{
+  g_err.clear();
+  if (!valid_codec(family, N, bits)) { set_err("unsupported codec (family %d, N %d, bits %d)", family, N, bits); return nullptr; }
+  if (!inBase || !items || count == 0 || count > 0x7fffffffull) { set_err("bad batch arguments"); return nullptr; }
+  BatchPlan plan;
+  if (!plan_batch(family, N, inBase, items, count, &plan)) return nullptr;
+  for (size_t i = 0; i < count; i++)
+    if (!plan.good[i]) { set_err("stream %zu of the batch is malformed", i); return nullptr; }
+  std::unique_ptr<hsr_stream, void (*)(hsr_stream *)> s(new hsr_stream, stream_release);
+  s->family = family; s->N = N; s->bits = bits; s->batch = true;
+  CU_TRY(cudaGetDevice(&s->device), return nullptr);
+  s->n = plan.outHi;           // the output buffer is addressed from outBase: it must hold outHi bytes
+  s->compLen = plan.inHi - plan.inLo;
+  s->inBase = plan.inLo;
+  s->inBytes = plan.inHi - plan.inLo;
+  s->outOffset = 0;
+  s->outBytes = plan.outHi;
+  CU_TRY(cudaMalloc(&s->dIn, (size_t)s->inBytes + 16), return nullptr);
+  s->ownsIn = true;
+  CU_TRY(cudaMemcpy(s->dIn, inBase + plan.inLo, (size_t)s->inBytes, cudaMemcpyHostToDevice), return nullptr);
+  if (family == HSR_BLOCK) {
+    for (auto &d : plan.descs) d.outOffset += plan.outLo; // decode_async passes outBase itself
+    s->numDescs = (uint32_t)plan.descs.size();
+    CU_TRY(cudaMalloc(&s->dDescs, plan.descs.size() * sizeof(BlockStreamDesc)), return nullptr);
+    CU_TRY(cudaMemcpy(s->dDescs, plan.descs.data(), plan.descs.size() * sizeof(BlockStreamDesc), cudaMemcpyHostToDevice), return nullptr);
+  } else {
+    s->blocks = std::move(plan.units);
+  }
+  if (!stream_finish(s.get())) return nullptr;
+  return s.release();
+}
+
 extern "C" uint64_t hsr_stream_decoded_length(const hsr_stream_t *s) { return s ? s->n : 0; }
 extern "C" uint64_t hsr_stream_shard_out_offset(const hsr_stream_t *s) { return s ? s->outOffset : 0; }
 extern "C" uint64_t hsr_stream_shard_out_bytes(const hsr_stream_t *s) { return s ? s->outBytes : 0; }
 extern "C" uint64_t hsr_stream_shard_in_bytes(const hsr_stream_t *s) { return s ? s->inBytes : 0; }
-extern "C" uint64_t hsr_stream_units(const hsr_stream_t *s) { return s ? (s->family == HSR_BLOCK ? 1 : s->blocks.size()) : 0; }
+extern "C" uint64_t hsr_stream_units(const hsr_stream_t *s) { return s ? (s->family == HSR_BLOCK ? (s->batch ? s->numDescs : 1) : s->blocks.size()) : 0; }
 extern "C" double hsr_stream_index_ms(const hsr_stream_t *s) { return s ? s->indexMs : 0.0; }
 
 extern "C" int hsr_stream_copy_index(const hsr_stream_t *s, hsr_block_t *blocks, size_t maxBlocks)
@@ -551,6 +664,8 @@ extern "C" int hsr_stream_decode_async(hsr_stream_t *s, void *dOutV, size_t outC
   const uint64_t need = local ? s->outBytes : s->n;
   if (outCapacity < need) { set_err("outCapacity %zu < %llu", outCapacity, (unsigned long long)need); return -1; }
   const uint64_t outBase = local ? s->outOffset : 0;
+  if (s->family == HSR_BLOCK && s->batch)
+    return launch_block_batch(s->N, s->bits, s->dIn, dOut, s->dDescs, s->numDescs, s->dCounter, nullptr, st);
   if (s->family == HSR_BLOCK)
     return launch_block_stream(s->N, s->bits, s->dIn, s->compLen, dOut, s->n, s->dCounter, st);
   return launch_units(s->N, s->bits, s->dIn, s->inBase, dOut, outBase, s->dBlocks, (uint32_t)s->blocks.size(), s->dCounter, st);
@@ -794,6 +909,86 @@ extern "C" size_t hsr_decode(int family, int N, int bits, const uint8_t *in, siz
     return 0;
   }
   return run_units_pipelined(c, N, bits, out, c->hBlocks, 0, (size_t)cnt, fl) ? (size_t)h.n : 0;
+}
+
+// Many independent streams of one codec in ONE launch: raw and block_ streams are a single recurrence each (one
+// warp), so a batch is the only way they fill a GPU; mt_ streams simply contribute all their blocks.
+extern "C" size_t hsr_decode_batch(int family, int N, int bits, const uint8_t *inBase, uint8_t *outBase, const hsr_batch_item_t *items,
+                                   size_t count, uint64_t *decodedLengths)
+{
+  g_err.clear();
+  if (!valid_codec(family, N, bits)) { set_err("unsupported codec (family %d, N %d, bits %d)", family, N, bits); return 0; }
+  if (!inBase || !outBase || !items || !decodedLengths) { set_err("null argument"); return 0; }
+  if (count == 0) return 0;
+  if (count > 0x7fffffffull) { set_err("too many streams"); return 0; }
+  int device = 0;
+  CU_TRY(cudaGetDevice(&device), return 0);
+  DeviceCtx *c = get_ctx(device);
+  if (!c) return 0;
+  std::lock_guard<std::mutex> lock(c->mu);
+
+  BatchPlan plan;
+  if (!plan_batch(family, N, inBase, items, count, &plan)) return 0;
+  for (size_t i = 0; i < count; i++) decodedLengths[i] = 0;
+  std::vector<Header> &hdr = plan.hdr;
+  std::vector<char> &good = plan.good;
+  std::vector<hsr_block_t> &units = plan.units;
+  std::vector<BlockStreamDesc> &descs = plan.descs;
+  std::vector<uint32_t> &descStream = plan.descStream;
+  const uint64_t inLo = plan.inLo, inHi = plan.inHi, outLo = plan.outLo, outHi = plan.outHi;
+
+  if (!grow(c->dIn, c->inCap, (size_t)(inHi - inLo) + 16)) return 0;
+  if (!grow(c->dOut, c->outCap, (size_t)(outHi - outLo) + 16)) return 0;
+  if (!grow(c->dCounters, c->countersCap, 4 + count)) return 0; // [0] counter, [1] status, [4..] per-stream status
+  uint32_t *dStreamStatus = c->dCounters + 4;
+  CU_TRY(cudaMemsetAsync(c->dCounters, 0, (4 + count) * sizeof(uint32_t), c->sRun), return 0);
+  CU_TRY(cudaMemcpyAsync(c->dIn, inBase + inLo, (size_t)(inHi - inLo), cudaMemcpyHostToDevice, c->sRun), return 0);
+  if (family == HSR_BLOCK) {
+    const size_t bytes = descs.size() * sizeof(BlockStreamDesc);
+    if (!grow(c->dBlocks, c->blocksCap, bytes / sizeof(hsr_block_t) + 1)) return 0;
+    CU_TRY(cudaMemcpyAsync(c->dBlocks, descs.data(), bytes, cudaMemcpyHostToDevice, c->sRun), return 0);
+    // per-stream status is indexed by the position in `descs`; map back below
+    if (launch_block_batch(N, bits, c->dIn, c->dOut, reinterpret_cast<const BlockStreamDesc *>(c->dBlocks), (uint32_t)descs.size(),
+                           c->dCounters, dStreamStatus, c->sRun) < 0)
+      return 0;
+  } else {
+    if (!grow(c->dBlocks, c->blocksCap, units.size())) return 0;
+    CU_TRY(cudaMemcpyAsync(c->dBlocks, units.data(), units.size() * sizeof(hsr_block_t), cudaMemcpyHostToDevice, c->sRun), return 0);
+    if (launch_units(N, bits, c->dIn, inLo, c->dOut, outLo, c->dBlocks, (uint32_t)units.size(), c->dCounters, c->sRun, dStreamStatus) < 0)
+      return 0;
+  }
+  std::vector<uint32_t> status(4 + count);
+  CU_TRY(cudaMemcpyAsync(status.data(), c->dCounters, (4 + count) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->sRun), return 0);
+  CU_TRY(cudaStreamSynchronize(c->sRun), return 0);
+
+  // copy back only streams that decoded cleanly, merging runs whose outputs are contiguous
+  size_t ok = 0;
+  if (family == HSR_BLOCK) {
+    std::vector<uint32_t> perStream(count, 0);
+    for (size_t k = 0; k < descStream.size(); k++) perStream[descStream[k]] = status[4 + k];
+    for (size_t i = 0; i < count; i++) status[4 + i] = perStream[i];
+  }
+  uint64_t runLo = 0, runHi = 0;
+  bool open = false;
+  auto flush = [&]() -> bool {
+    if (!open) return true;
+    CU_TRY(cudaMemcpyAsync(outBase + runLo, c->dOut + (runLo - outLo), (size_t)(runHi - runLo), cudaMemcpyDeviceToHost, c->sOut), return false);
+    open = false;
+    return true;
+  };
+  for (size_t i = 0; i < count; i++) {
+    if (!good[i] || status[4 + i]) continue;
+    decodedLengths[i] = hdr[i].n;
+    ok++;
+    const uint64_t lo = items[i].outOffset, hi = lo + hdr[i].n;
+    if (open && lo == runHi) { runHi = hi; continue; }
+    if (!flush()) return 0;
+    runLo = lo; runHi = hi; open = true;
+  }
+  if (!flush()) return 0;
+  CU_TRY(cudaStreamSynchronize(c->sOut), return 0);
+  if (ok != count) set_err("%zu of %zu streams were malformed", count - ok, count);
+  return ok;
 }
 
 extern "C" size_t hsr_decode_mt_multi(int N, int bits, const uint8_t *in, size_t inLength, uint8_t *out, size_t outCapacity,

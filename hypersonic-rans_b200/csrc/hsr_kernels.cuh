@@ -14,21 +14,33 @@ struct DecodeParams {
   uint64_t outBase;
   const hsr_block_t *blocks;
   uint32_t numBlocks;
-  uint32_t *counter; // [0] work counter, [1] status bits
+  uint32_t *counter;      // [0] work counter, [1] status bits (OR over all units)
+  uint32_t *streamStatus; // optional: status bits per stream, indexed by hsr_block_t::reserved (batch decode)
 };
 
-struct BlockStreamParams { // block_ framing: one sequential recurrence
+// block_ framing: every stream is one sequential recurrence; a batch gives one warp to each stream
+struct BlockStreamDesc {
+  uint64_t inOffset, inLength; // stream bytes at in + inOffset
+  uint64_t outOffset, n;       // decoded bytes at out + outOffset
+};
+
+struct BlockStreamParams {
   const uint8_t *in;
-  uint64_t inLength;
   uint8_t *out;
-  uint64_t n;
-  uint32_t *counter; // [1] status bits
+  const BlockStreamDesc *streams; // device array, or nullptr: `single` is the only stream
+  BlockStreamDesc single;
+  uint32_t numStreams;
+  uint32_t *counter;      // [0] work counter, [1] status bits
+  uint32_t *streamStatus; // optional, per stream
 };
 
-__device__ __forceinline__ void raise(uint32_t *counter, uint32_t bits, uint32_t lane)
+__device__ __forceinline__ void raise(uint32_t *counter, uint32_t *streamStatus, uint32_t stream, uint32_t bits, uint32_t lane)
 {
-  if (lane == 0)
+  if (lane == 0) {
     atomicOr(counter + 1, bits);
+    if (streamStatus)
+      atomicOr(streamStatus + stream, bits);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- mt_ / raw
@@ -62,6 +74,7 @@ __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
     const uint64_t count = __ldg(&blk->count);
     const uint32_t kind = __ldg(&blk->kind);
     const uint32_t tailCount = __ldg(&blk->tail);
+    const uint32_t streamId = __ldg(&blk->reserved);
     uint8_t *out = p.out + (outOffset - p.outBase);
 
     if (kind == 1u) {
@@ -77,7 +90,7 @@ __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
 
     const TableInfo info = build_tables<BITS, N, TK>(sw, countsPtr, lane);
     if (!info.ok) {
-      raise(p.counter, HSR_ERR_HIST, lane);
+      raise(p.counter, p.streamStatus, streamId, HSR_ERR_HIST, lane);
       continue;
     }
 
@@ -96,7 +109,7 @@ __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
       dec.tail(x0, x1, ring, outLane + rows * N, lanePos, tailCount, lane, ltMask);
     ring.drain();
     if (ring.cursor() > ring.glimit)
-      raise(p.counter, HSR_ERR_OVERRUN, lane);
+      raise(p.counter, p.streamStatus, streamId, HSR_ERR_OVERRUN, lane);
   }
 }
 
@@ -106,20 +119,18 @@ __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
 // every block; each block header sits in-band at the word cursor, so block k+1 cannot be located before block k
 // has been decoded. One warp walks the whole stream, rebuilding its tables between sections.
 template <int BITS, int N, int TK>
-__device__ __forceinline__ void block_kernel_body(const BlockStreamParams &p)
+__device__ __forceinline__ void block_stream_decode(const BlockStreamParams &p, const BlockStreamDesc &d, uint32_t streamId, uint32_t sw,
+                                                    uint32_t lane, uint32_t ltMask, uint32_t lanePos)
 {
   using L = WarpLayout<BITS, N, TK>;
-  const uint32_t sw = declare_smem<L::kBytes>();
-  const uint32_t lane = lane_id();
-  const uint32_t ltMask = lanemask_lt();
-  const uint32_t lanePos = idx2idx_lane(lane);
 
   Decoder<BITS, N, TK> dec;
   dec.init(sw);
   TableInfo info{false, false, false};
 
-  const uint8_t *in = p.in;
-  const uint8_t *streamEnd = p.in + p.inLength;
+  const uint8_t *in = p.in + d.inOffset;
+  const uint8_t *streamEnd = in + d.inLength;
+  uint8_t *outBase = p.out + d.outOffset;
   uint64_t pos = 16;
   uint32_t x0 = ldg_u32_a2(in + pos + 4 * lane);
   uint32_t x1 = 0;
@@ -127,7 +138,7 @@ __device__ __forceinline__ void block_kernel_body(const BlockStreamParams &p)
     x1 = ldg_u32_a2(in + pos + 4 * (lane + 32));
   pos += 4 * N;
 
-  const uint64_t n = p.n;
+  const uint64_t n = d.n;
   const uint64_t outLengthInStates = n - N + 1;
   uint64_t i = 0;
   bool haveHist = false;
@@ -135,8 +146,8 @@ __device__ __forceinline__ void block_kernel_body(const BlockStreamParams &p)
   const uint32_t sRing = sw + L::kOffRing;
 
   do {
-    if (pos + 8 > p.inLength) {
-      raise(p.counter, HSR_ERR_OVERRUN, lane);
+    if (pos + 8 > d.inLength) {
+      raise(p.counter, p.streamStatus, streamId, HSR_ERR_OVERRUN, lane);
       return;
     }
     const uint64_t v = ldg_u64_a2(in + pos);
@@ -145,19 +156,19 @@ __device__ __forceinline__ void block_kernel_body(const BlockStreamParams &p)
       const uint32_t symbol = (uint32_t)(v >> 54) & 0xffu;
       const uint64_t size = v & ((1ull << 54) - 1);
       if (size > n - i) {
-        raise(p.counter, HSR_ERR_BOUNDS, lane);
+        raise(p.counter, p.streamStatus, streamId, HSR_ERR_BOUNDS, lane);
         return;
       }
-      warp_fill(p.out + i, symbol, size, lane);
+      warp_fill(outBase + i, symbol, size, lane);
       i += size;
     } else {
-      if (pos + 512 > p.inLength) {
-        raise(p.counter, HSR_ERR_OVERRUN, lane);
+      if (pos + 512 > d.inLength) {
+        raise(p.counter, p.streamStatus, streamId, HSR_ERR_OVERRUN, lane);
         return;
       }
       info = build_tables<BITS, N, TK>(sw, in + pos, lane); // :69-76
       if (!info.ok) {
-        raise(p.counter, HSR_ERR_HIST, lane);
+        raise(p.counter, p.streamStatus, streamId, HSR_ERR_HIST, lane);
         return;
       }
       haveHist = true;
@@ -167,15 +178,15 @@ __device__ __forceinline__ void block_kernel_body(const BlockStreamParams &p)
       if (blockEnd > outLengthInStates)
         blockEnd = outLengthInStates;
       else if (blockEnd & (N - 1)) {
-        raise(p.counter, HSR_ERR_ALIGN, lane);
+        raise(p.counter, p.streamStatus, streamId, HSR_ERR_ALIGN, lane);
         return;
       }
       const uint64_t rows = blockEnd > i ? (blockEnd - i + N - 1) / N : 0;
       ring.start(sRing, in + pos, streamEnd, lane);
-      dec.rows(info, x0, x1, ring, p.out + i + lanePos, rows, lane, ltMask);
+      dec.rows(info, x0, x1, ring, outBase + i + lanePos, rows, lane, ltMask);
       ring.drain();
       if (ring.cursor() > ring.glimit) {
-        raise(p.counter, HSR_ERR_OVERRUN, lane);
+        raise(p.counter, p.streamStatus, streamId, HSR_ERR_OVERRUN, lane);
         return;
       }
       pos = (uint64_t)(ring.gbase - in) + ring.cursor();
@@ -190,12 +201,40 @@ __device__ __forceinline__ void block_kernel_body(const BlockStreamParams &p)
 
   if (i < n) { // :98-139
     if (!haveHist) {
-      raise(p.counter, HSR_ERR_HIST, lane);
+      raise(p.counter, p.streamStatus, streamId, HSR_ERR_HIST, lane);
       return;
     }
     ring.start(sRing, in + pos, streamEnd, lane);
-    dec.tail(x0, x1, ring, p.out + i + lanePos, lanePos, (uint32_t)(n - i), lane, ltMask);
+    dec.tail(x0, x1, ring, outBase + i + lanePos, lanePos, (uint32_t)(n - i), lane, ltMask);
     ring.drain();
+  }
+}
+
+template <int BITS, int N, int TK>
+__device__ __forceinline__ void block_kernel_body(const BlockStreamParams &p)
+{
+  using L = WarpLayout<BITS, N, TK>;
+  const uint32_t sw = declare_smem<L::kBytes>();
+  const uint32_t lane = lane_id();
+  const uint32_t ltMask = lanemask_lt();
+  const uint32_t lanePos = idx2idx_lane(lane);
+  if (p.streams == nullptr) {
+    block_stream_decode<BITS, N, TK>(p, p.single, 0u, sw, lane, ltMask, lanePos);
+    return;
+  }
+  for (;;) { // persistent: streams are handed out by an atomic counter
+    uint32_t s = 0;
+    if (lane == 0)
+      s = atomicAdd(p.counter, 1u);
+    s = __shfl_sync(kFull, s, 0);
+    if (s >= p.numStreams)
+      break;
+    BlockStreamDesc d;
+    d.inOffset = __ldg(&p.streams[s].inOffset);
+    d.inLength = __ldg(&p.streams[s].inLength);
+    d.outOffset = __ldg(&p.streams[s].outOffset);
+    d.n = __ldg(&p.streams[s].n);
+    block_stream_decode<BITS, N, TK>(p, d, s, sw, lane, ltMask, lanePos);
   }
 }
 

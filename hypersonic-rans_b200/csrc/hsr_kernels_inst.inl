@@ -13,7 +13,7 @@ namespace hsr {
 #define HSR_DEFINE(BITS, TK)                                                                                          \
   __global__ void __launch_bounds__(32, 32) HSR_NAME(units_n, BITS, TK)(DecodeParams p)                               \
   { units_kernel_body<BITS, HSR_N, TK>(p); }                                                                          \
-  __global__ void __launch_bounds__(32, 1) HSR_NAME(block_n, BITS, TK)(BlockStreamParams p)                           \
+  __global__ void __launch_bounds__(32, 16) HSR_NAME(block_n, BITS, TK)(BlockStreamParams p)                           \
   { block_kernel_body<BITS, HSR_N, TK>(p); }
 
 #define HSR_ENTRY(BITS, TK)                                                                                           \

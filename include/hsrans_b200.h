@@ -56,6 +56,11 @@ size_t hsr_capacity(int family, int stateCount, size_t inputSize);
 void *hsr_host_alloc(size_t bytes);
 void hsr_host_free(void *p);
 
+/* One stream of a batch (hsr_decode_batch, hsr_stream_upload_batch): byte ranges relative to the batch's base pointers. */
+typedef struct hsr_batch_item {
+  uint64_t inOffset, inLength, outOffset, outCapacity;
+} hsr_batch_item_t;
+
 /* ------------------------------------------------------------------------------------------------ drop-in decode */
 
 /* Host-pointer decode: H2D, index (mt_), kernels, D2H, synchronise. Replaces every function of type
@@ -74,6 +79,16 @@ size_t hsr_decode_mt_multi(int stateCount, int bits, const uint8_t *pInData, siz
                            size_t outCapacity, const int *devices, int deviceCount);
 
 int hsr_set_device(int device);
+
+/* Many independent streams of ONE codec in one launch. A raw or block_ stream is a single 32/64-lane recurrence
+ * (one warp of parallelism, SURVEY.md finding 1), so batching streams is what fills the GPU for those codecs — the
+ * analogue of running the reference's decoder on many files from many threads. Stream i occupies
+ * inBase[inOffset, inOffset + inLength) and decodes to outBase[outOffset, outOffset + n) with n <= outCapacity;
+ * output ranges must not overlap. decodedLengths[i] receives n, or 0 if stream i is malformed (the others are still
+ * decoded). Returns the number of streams decoded. Each stream is checked like hsr_decode checks its input. */
+
+size_t hsr_decode_batch(int family, int stateCount, int bits, const uint8_t *inBase, uint8_t *outBase,
+                        const hsr_batch_item_t *items, size_t count, uint64_t *decodedLengths);
 
 /* ------------------------------------------------------------------------------------------------ mt_ index (host) */
 
@@ -113,6 +128,11 @@ hsr_stream_t *hsr_stream_upload(int family, int stateCount, int bits, const uint
 /* Wrap compressed bytes that already live in device memory (16-byte aligned, readable up to inLength).
  * mt_: the header chain is walked by a device kernel (serial; see hsr_stream_index_ms). */
 hsr_stream_t *hsr_stream_from_device(int family, int stateCount, int bits, const void *dIn, size_t inLength);
+/* A batch of independent streams of one codec (see hsr_decode_batch) made resident for repeated decoding. Offsets in
+ * `items` are relative to inBase; the decode writes stream i at dOut + items[i].outOffset, so dOut must hold
+ * hsr_stream_decoded_length() = max(outOffset + n) bytes. Fails if any stream of the batch is malformed. */
+hsr_stream_t *hsr_stream_upload_batch(int family, int stateCount, int bits, const uint8_t *inBase, const hsr_batch_item_t *items,
+                                      size_t count);
 void hsr_stream_free(hsr_stream_t *s);
 
 uint64_t hsr_stream_decoded_length(const hsr_stream_t *s); /* header n (whole stream) */

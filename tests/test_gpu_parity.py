@@ -161,6 +161,43 @@ def test_prepared_stream_device_api_and_shards(gpu, golden):
         p2.free()
 
 
+@pytest.mark.parametrize("fam", [ck.RAW, ck.BLOCK, ck.MT])
+def test_batch_of_independent_streams(gpu, golden, fam):
+    """One launch over many streams: the only way the single-recurrence codecs fill a GPU."""
+    states, bits = {ck.RAW: (64, 12), ck.BLOCK: (32, 10), ck.MT: (64, 15)}[fam]
+    names = ["multi", "small", "tiny65", "skew", "flat", "tiny127"]
+    if fam == ck.MT:
+        names = ["multi", "small", "tiny65"]
+    streams, datas = [], []
+    for k in range(24):
+        name = names[k % len(names)]
+        key = f"stream/{name}/{fam}/{states}/{bits}"
+        if key not in golden:
+            continue
+        streams.append(golden[key]); datas.append(golden[f"in/{name}"])
+    bad_index = 3
+    streams[bad_index] = streams[bad_index].copy()
+    off = {ck.RAW: 16 + 9, ck.BLOCK: 16 + 4 * states + 8 + 9, ck.MT: 16 + 16 + 4 * states + 9}[fam]
+    streams[bad_index][off] ^= 0x40   # break one histogram: that stream must fail alone
+    items, in_parts, pos_in, pos_out = [], [], 0, 0
+    for s, d in zip(streams, datas):
+        pad = (-pos_in) % 16
+        in_parts.append(np.zeros(pad, np.uint8)); pos_in += pad
+        items.append((pos_in, s.size, pos_out, d.size))
+        in_parts.append(s); pos_in += s.size
+        pos_out += d.size + 7  # leave small gaps: nothing may be written there
+    in_base = np.concatenate(in_parts)
+    out_base = np.full(pos_out + 64, 0xCC, np.uint8)
+    ok, lengths = gpu.decode_batch(fam, states, bits, in_base, out_base, items)
+    assert ok == len(items) - 1
+    for k, ((io, il, oo, oc), d) in enumerate(zip(items, datas)):
+        if k == bad_index:
+            assert lengths[k] == 0 and np.all(out_base[oo:oo + oc] == 0xCC)
+            continue
+        assert lengths[k] == d.size and np.array_equal(out_base[oo:oo + d.size], d), k
+        assert np.all(out_base[oo + d.size: oo + d.size + 7] == 0xCC)
+
+
 def test_multi_device_entry_point_on_one_gpu(gpu, golden):
     data = golden["in/multi"]
     n, out = gpu.decode_mt_multi(64, 15, golden["stream/multi/2/64/15"], data.size, devices=[0, 0])
