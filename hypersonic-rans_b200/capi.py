@@ -62,6 +62,9 @@ SIGNATURES = {
     "hsr_observe_hist_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "hsr_normalize_hist_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hsr_make_hist_segments_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
+    "hsr_encode_mt": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "hsr_encode_mt_device": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "hsr_encode_mt_bound": (C.c_size_t, [C.c_int, C.c_size_t, C.c_size_t]),
     "hsr_synth_zipf": (C.c_int, [C.c_void_p, C.c_size_t, C.c_double, C.c_uint64, C.c_size_t]),
 }
 
@@ -283,6 +286,28 @@ def normalize_hist_device(d_hist: int, data_bytes: int, bits: int, d_count: int,
 
 def make_hist_segments_device(d_data: int, size: int, segment_bytes: int, bits: int, d_counts: int, cuda_stream: int = 0) -> int:
     return lib().hsr_make_hist_segments_device(d_data, size, segment_bytes, bits, d_counts, cuda_stream)
+
+
+def encode_mt(state_count: int, bits: int, data, block_size: int = 0) -> np.ndarray:
+    """Device mt_ encoder (hsr_encode_mt): returns the compressed stream as a uint8 array; raises on failure."""
+    src = _as_u8(data)
+    bound = lib().hsr_encode_mt_bound(state_count, src.size, block_size)
+    if bound == 0:
+        raise HsrError("hsr_encode_mt_bound: unsupported arguments")
+    out = np.empty(bound, np.uint8)
+    n = lib().hsr_encode_mt(state_count, bits, _ptr(src), src.size, _ptr(out), bound, block_size)
+    if n == 0:
+        raise HsrError(f"hsr_encode_mt failed: {last_error()}")
+    return out[:n].copy()
+
+
+def encode_mt_device(state_count: int, bits: int, d_in: int, length: int, d_out: int, out_capacity: int, block_size: int = 0,
+                     cuda_stream: int = 0) -> int:
+    return lib().hsr_encode_mt_device(state_count, bits, d_in, length, d_out, out_capacity, block_size, cuda_stream)
+
+
+def encode_mt_bound(state_count: int, length: int, block_size: int = 0) -> int:
+    return lib().hsr_encode_mt_bound(state_count, length, block_size)
 
 
 def synth_zipf(n: int, s: float = 1.0, seed: int = 42, segment_bytes: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:

@@ -171,6 +171,24 @@ int hsr_normalize_hist_device(const uint32_t *dHist, size_t dataBytes, int bits,
 int hsr_make_hist_segments_device(const void *dData, size_t size, size_t segmentBytes, int bits,
                                   uint16_t *dSymbolCounts, void *cudaStream);
 
+/* ------------------------------------------------------------------------------------------------ mt_ encoder (device) */
+
+/* Produces an mt_rANS32xN_16w stream on the GPU. Same stream format as mt_rANS32xNN_16w_encode_<b>
+ * (src/mt_rANS32x64_16w_encode.cpp:140-380; signature src/mt_rANS32x64_16w.h:9-14) and the same per-block histogram
+ * (observe_hist + normalize_hist over the block's bytes), but with a FIXED block size (0 = 65536 = the reference's
+ * MinBlockSize; a multiple of the state count, at most 2^25) and every block encoded from fresh states, so blocks
+ * are independent GPU work and the result always has ~n / blockSize blocks whatever the data's stationarity. Any
+ * reference decoder decodes it; for inputs of at most one block it is byte-identical to the reference encoder's
+ * output (constant inputs excepted: no single-symbol run blocks are emitted). Returns the compressed length, 0 on
+ * error (length < stateCount, outCapacity too small, no GPU). */
+size_t hsr_encode_mt(int stateCount, int bits, const uint8_t *pInData, size_t length, uint8_t *pOutData, size_t outCapacity,
+                     size_t blockSize);
+/* Device-pointer form; dOut should hold hsr_encode_mt_bound() bytes. Synchronises cudaStream once. */
+size_t hsr_encode_mt_device(int stateCount, int bits, const void *dIn, size_t length, void *dOut, size_t outCapacity, size_t blockSize,
+                            void *cudaStream);
+/* Hard upper bound of the stream size for `length` input bytes (one 16-bit word per symbol + headers). */
+size_t hsr_encode_mt_bound(int stateCount, size_t length, size_t blockSize);
+
 /* ------------------------------------------------------------------------------------------------ synthetic inputs */
 
 /* Deterministic Zipf(s) bytes over 256 symbols. segmentBytes == 0: one rank->byte permutation
