@@ -264,6 +264,51 @@ def single_recurrence_extras(pkg, torch, a):
                                  "algorithmic_GBps": round((total + in_base.size) / ms / 1e6, 1)}
         ps.free()
         del out2
+
+    # device-side producer (hsr_encode_mt_device) and the histogram kernels, on the same 1 GB of bytes
+    n = a.size
+    for shape, seg in (("pw64k", 65536), ("iid", 0)):
+        data = pkg.synth_zipf(n, a.zipf, seed=42, segment_bytes=seg)
+        d_in = torch.from_numpy(data).cuda()
+        bound = pkg.encode_mt_bound(a.states, n)
+        d_out = torch.empty(bound, dtype=torch.uint8, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        comp = pkg.encode_mt_device(a.states, a.bits, d_in.data_ptr(), n, d_out.data_ptr(), bound, 0, st)   # warm-up, sizes scratch
+        times = []
+        for _ in range(5):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            comp = pkg.encode_mt_device(a.states, a.bits, d_in.data_ptr(), n, d_out.data_ptr(), bound, 0, st)
+            torch.cuda.synchronize(); times.append(time.perf_counter() - t0)
+        ps = pkg.PreparedStream.from_device(2, a.states, a.bits, d_out.data_ptr(), comp)
+        out3 = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
+        ps.decode_async(out3.data_ptr(), n, st)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ps.decode_async(out3.data_ptr(), n, st)
+        e1.record()
+        torch.cuda.synchronize()
+        dec_ms = e0.elapsed_time(e1) / 5
+        ok = comp > 0 and ps.status() == 0 and bool(torch.equal(out3[:n], d_in))
+        res[f"device_encoder_{shape}"] = {"encode_GBps": round(n / min(times) / 1e9, 2), "encode_ms": round(min(times) * 1e3, 3),
+                                          "compressed_bytes": int(comp), "blocks": int(ps.units), "round_trip_bit_exact": ok,
+                                          "decode_GBps_of_this_stream": round(n / dec_ms / 1e6, 2)}
+        ps.free()
+        if shape == "pw64k":
+            hist = torch.zeros(256, dtype=torch.int32, device="cuda")
+            counts = torch.zeros(((n + 65535) // 65536, 256), dtype=torch.int16, device="cuda")
+            for label, fn in (("observe_hist", lambda: pkg.observe_hist_device(d_in.data_ptr(), n, hist.data_ptr(), st)),
+                              ("segment_hists_64k", lambda: pkg.make_hist_segments_device(d_in.data_ptr(), n, 65536, a.bits, counts.data_ptr(), st))):
+                fn(); torch.cuda.synchronize()
+                e0.record()
+                for _ in range(5):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 5
+                res[label] = {"GBps": round(n / ms / 1e6, 1), "ms": round(ms, 3)}
+        del d_in, d_out, out3
     return res
 
 

@@ -54,6 +54,19 @@ inline size_t cuda_block_rANS32x64_16w_capacity(const size_t inputSize) { return
 inline size_t cuda_mt_rANS32x32_16w_capacity(const size_t inputSize) { return hsr_capacity(HSR_MT, 32, inputSize); }
 inline size_t cuda_mt_rANS32x64_16w_capacity(const size_t inputSize) { return hsr_capacity(HSR_MT, 64, inputSize); }
 
+// Device producers with the reference's mt_ encoder signature (src/mt_rANS32x64_16w.h:9-14):
+//     size_t mt_rANS32x64_16w_encode_<b>(const uint8_t *pInData, const size_t length, uint8_t *pOutData, const size_t outCapacity)
+// Same stream format, fixed 64 KiB blocks (see hsr_encode_mt); decodable by every reference mt_ decoder.
+#define HSR_B200_ENCODER(states, bits)                                                                                           \
+  inline size_t cuda_mt_rANS32x##states##_16w_encode_##bits(const uint8_t *pInData, const size_t length, uint8_t *pOutData,     \
+                                                            const size_t outCapacity)                                           \
+  {                                                                                                                              \
+    return hsr_encode_mt(states, bits, pInData, length, pOutData, outCapacity, 0);                                               \
+  }
+HSR_B200_ENCODER(32, 15) HSR_B200_ENCODER(32, 14) HSR_B200_ENCODER(32, 13) HSR_B200_ENCODER(32, 12) HSR_B200_ENCODER(32, 11) HSR_B200_ENCODER(32, 10)
+HSR_B200_ENCODER(64, 15) HSR_B200_ENCODER(64, 14) HSR_B200_ENCODER(64, 13) HSR_B200_ENCODER(64, 12) HSR_B200_ENCODER(64, 11) HSR_B200_ENCODER(64, 10)
+#undef HSR_B200_ENCODER
+
 // hist.h:54-58 twins on the device (bit-exact): make_hist = observe_hist + normalize_hist.
 struct cuda_hist_t { // same layout as hist_t, src/hist.h:6-10
   uint16_t symbolCount[256];

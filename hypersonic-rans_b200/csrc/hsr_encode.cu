@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -47,16 +48,18 @@ __device__ __forceinline__ uint64_t block_end(const EncPlan &pl, uint32_t k) { r
 
 // ---------------------------------------------------------------------------------------------- per-block histograms
 
-__global__ void __launch_bounds__(kHistThreads) enc_hist_kernel(const uint8_t *data, EncPlan pl, int bits, uint16_t *counts)
+constexpr int kSegWarps = 4; // warps per CTA in the per-block histogram kernels
+
+__global__ void __launch_bounds__(kSegWarps * 32) enc_hist_kernel(const uint8_t *data, EncPlan pl, int bits, uint16_t *counts)
 {
-  __shared__ uint32_t sPriv[kHistWarps][256];
-  __shared__ uint32_t sOut[256];
-  __shared__ uint16_t sCapped[256];
-  __shared__ uint8_t sIdx[256];
-  for (uint32_t k = blockIdx.x; k < pl.numBlocks; k += gridDim.x) {
+  __shared__ uint32_t sHist[kSegWarps][256];
+  __shared__ uint16_t sCapped[kSegWarps][256];
+  __shared__ uint8_t sIdx[kSegWarps][256];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (uint32_t k = blockIdx.x * kSegWarps + warp; k < pl.numBlocks; k += gridDim.x * kSegWarps) {
     const uint64_t begin = block_begin(pl, k), end = block_end(pl, k);
-    cta_observe(data, begin, end, sPriv, sOut, 0, 1);
-    cta_normalize(sOut, end - begin, bits, sCapped, sIdx, counts + (uint64_t)k * 256, nullptr); // :209-210
+    warp_observe(data, begin, end, sHist[warp], lane);
+    warp_normalize(sHist[warp], end - begin, bits, sCapped[warp], sIdx[warp], counts + (uint64_t)k * 256, lane); // :209-210
   }
 }
 
@@ -72,7 +75,7 @@ struct EncSym {
 };
 
 template <int BITS, int N>
-__global__ void __launch_bounds__(32, 16) enc_block_kernel(const uint8_t *in, EncPlan pl, const uint16_t *counts, uint8_t *scratch,
+__global__ void __launch_bounds__(32, 32) enc_block_kernel(const uint8_t *__restrict__ in, EncPlan pl, const uint16_t *counts, uint8_t *scratch,
                                                            EncBlockMeta *meta, uint32_t *counter)
 {
   __shared__ __align__(16) EncSym sSym[256];
@@ -162,15 +165,27 @@ __global__ void __launch_bounds__(32, 16) enc_block_kernel(const uint8_t *in, En
       const bool a0 = lanePos < tailLen;
       step(x0, a0 ? row[lanePos] : 0u, a0);
     }
-    for (uint32_t r = rows; r-- > 0;) {
-      const uint8_t *row = src + (uint64_t)r * N;
-      if constexpr (N == 64) {
-        const uint32_t s1 = row[lanePos + 32u];
-        const uint32_t s0 = row[lanePos];
-        step(x1, s1, true);
+    // rows are independent of the states: keep the next kAhead rows' symbols in flight while the current one encodes
+    constexpr int kAhead = 4;
+    uint32_t q0[kAhead], q1[kAhead];
+#pragma unroll
+    for (int a = 0; a < kAhead; a++) {
+      const int64_t r = (int64_t)rows - 1 - a;
+      const uint8_t *row = src + (uint64_t)(r < 0 ? 0 : r) * N;
+      q0[a] = __ldg(row + lanePos);
+      q1[a] = N == 64 ? __ldg(row + lanePos + 32u) : 0u;
+    }
+    for (int64_t r = (int64_t)rows - 1; r >= 0; r -= kAhead) {
+#pragma unroll
+      for (int a = 0; a < kAhead; a++) {
+        if (r - a < 0) break;
+        const uint32_t s0 = q0[a], s1 = q1[a];
+        const int64_t rn = r - a - kAhead; // refill this slot with the row kAhead further down
+        const uint8_t *row = src + (uint64_t)(rn < 0 ? 0 : rn) * N;
+        q0[a] = __ldg(row + lanePos);
+        if constexpr (N == 64) q1[a] = __ldg(row + lanePos + 32u);
+        if constexpr (N == 64) step(x1, s1, true);
         step(x0, s0, true);
-      } else {
-        step(x0, row[lanePos], true);
       }
     }
 
@@ -300,17 +315,51 @@ bool make_plan(int N, uint64_t n, size_t blockSize, EncPlan *pl)
   return true;
 }
 
+// Scratch reused across calls (grow-only, one set per device): histograms, per-block word slots, block metadata.
 struct EncScratch {
+  int device = -1;
   uint16_t *dCounts = nullptr;
   uint8_t *dScratch = nullptr;
   EncBlockMeta *dMeta = nullptr;
   uint64_t *dOffsets = nullptr;
   uint32_t *dCounter = nullptr;
-  ~EncScratch()
+  size_t blocksCap = 0, scratchCap = 0;
+  std::mutex mu;
+
+  bool ensure(size_t blocks, size_t scratchBytes)
   {
-    cudaFree(dCounts); cudaFree(dScratch); cudaFree(dMeta); cudaFree(dOffsets); cudaFree(dCounter);
+    if (blocks > blocksCap) {
+      cudaFree(dCounts); cudaFree(dMeta); cudaFree(dOffsets);
+      dCounts = nullptr; dMeta = nullptr; dOffsets = nullptr; blocksCap = 0;
+      const size_t want = blocks + blocks / 8 + 16;
+      if (cudaMalloc(&dCounts, want * 512) != cudaSuccess || cudaMalloc(&dMeta, want * sizeof(EncBlockMeta)) != cudaSuccess ||
+          cudaMalloc(&dOffsets, (want + 1) * 8) != cudaSuccess)
+        return false;
+      blocksCap = want;
+    }
+    if (scratchBytes > scratchCap) {
+      cudaFree(dScratch);
+      dScratch = nullptr; scratchCap = 0;
+      if (cudaMalloc(&dScratch, scratchBytes + scratchBytes / 8) != cudaSuccess) return false;
+      scratchCap = scratchBytes + scratchBytes / 8;
+    }
+    if (!dCounter && cudaMalloc(&dCounter, 16) != cudaSuccess) return false;
+    return true;
   }
 };
+
+EncScratch *scratch_for_device(int device)
+{
+  static std::mutex mu;
+  static std::vector<EncScratch *> all;
+  std::lock_guard<std::mutex> lock(mu);
+  for (EncScratch *s : all)
+    if (s->device == device) return s;
+  EncScratch *s = new EncScratch;
+  s->device = device;
+  all.push_back(s);
+  return s;
+}
 
 } // namespace
 
@@ -333,20 +382,20 @@ extern "C" size_t hsr_encode_mt_device(int N, int bits, const void *dInV, size_t
   cudaStream_t st = static_cast<cudaStream_t>(cudaStream);
   const uint8_t *dIn = static_cast<const uint8_t *>(dInV);
   uint8_t *dOut = static_cast<uint8_t *>(dOutV);
-  EncScratch sc;
-  if (cudaMalloc(&sc.dCounts, (size_t)pl.numBlocks * 512) != cudaSuccess || cudaMalloc(&sc.dScratch, (size_t)pl.numBlocks * pl.slotBytes) != cudaSuccess ||
-      cudaMalloc(&sc.dMeta, (size_t)pl.numBlocks * sizeof(EncBlockMeta)) != cudaSuccess ||
-      cudaMalloc(&sc.dOffsets, ((size_t)pl.numBlocks + 1) * 8) != cudaSuccess || cudaMalloc(&sc.dCounter, 16) != cudaSuccess) {
-    (void)cudaGetLastError();
-    return 0;
-  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  EncScratch &sc = *scratch_for_device(dev);
+  std::lock_guard<std::mutex> lock(sc.mu);
+  if (!sc.ensure(pl.numBlocks, (size_t)pl.numBlocks * pl.slotBytes)) {
+    (void)cudaGetLastError();
+    return 0;
+  }
   cudaMemsetAsync(sc.dCounter, 0, 16, st);
   const unsigned gridH = (unsigned)std::min<uint64_t>(pl.numBlocks, (uint64_t)sms * 8);
-  enc_hist_kernel<<<gridH, kHistThreads, 0, st>>>(dIn, pl, bits, sc.dCounts);
-  const unsigned gridE = (unsigned)std::min<uint64_t>(pl.numBlocks, (uint64_t)sms * 16);
+  const unsigned gridS = (unsigned)std::min<uint64_t>((pl.numBlocks + kSegWarps - 1) / kSegWarps, (uint64_t)sms * 16);
+  enc_hist_kernel<<<gridS, kSegWarps * 32, 0, st>>>(dIn, pl, bits, sc.dCounts);
+  const unsigned gridE = (unsigned)std::min<uint64_t>(pl.numBlocks, (uint64_t)sms * 32);
   if (N == 32) launch_encode_n<32>(bits, dIn, pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dCounter, gridE, st);
   else launch_encode_n<64>(bits, dIn, pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dCounter, gridE, st);
   enc_scan_kernel<<<1, 1024, 0, st>>>(sc.dMeta, pl.numBlocks, 16 + 4 * (uint32_t)N + 512, sc.dOffsets);

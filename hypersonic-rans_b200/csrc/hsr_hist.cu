@@ -36,20 +36,21 @@ __global__ void __launch_bounds__(kHistThreads) normalize_kernel(const uint32_t 
   cta_normalize(sHist, dataBytes, bits, sCapped, sIdx, symbolCount, cumul);
 }
 
-// one CTA per segment: count the segment's bytes, normalise, write its 256 u16 counts
-__global__ void __launch_bounds__(kHistThreads) segments_kernel(const uint8_t *data, uint64_t size, uint64_t segmentBytes,
-                                                                int bits, uint16_t *symbolCounts)
+// one WARP per segment: count the segment's bytes, normalise, write its 256 u16 counts
+constexpr int kSegWarps = 4;
+__global__ void __launch_bounds__(kSegWarps * 32) segments_kernel(const uint8_t *data, uint64_t size, uint64_t segmentBytes, int bits,
+                                                                  uint16_t *symbolCounts)
 {
-  __shared__ uint32_t sPriv[kHistWarps][256];
-  __shared__ uint32_t sOut[256];
-  __shared__ uint16_t sCapped[256];
-  __shared__ uint8_t sIdx[256];
+  __shared__ uint32_t sHist[kSegWarps][256];
+  __shared__ uint16_t sCapped[kSegWarps][256];
+  __shared__ uint8_t sIdx[kSegWarps][256];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint64_t segments = (size + segmentBytes - 1) / segmentBytes;
-  for (uint64_t seg = blockIdx.x; seg < segments; seg += gridDim.x) {
+  for (uint64_t seg = (uint64_t)blockIdx.x * kSegWarps + warp; seg < segments; seg += (uint64_t)gridDim.x * kSegWarps) {
     const uint64_t begin = seg * segmentBytes;
     const uint64_t end = begin + segmentBytes < size ? begin + segmentBytes : size;
-    cta_observe(data, begin, end, sPriv, sOut, 0, 1);
-    cta_normalize(sOut, end - begin, bits, sCapped, sIdx, symbolCounts + seg * 256, nullptr);
+    warp_observe(data, begin, end, sHist[warp], lane);
+    warp_normalize(sHist[warp], end - begin, bits, sCapped[warp], sIdx[warp], symbolCounts + seg * 256, lane);
   }
 }
 
@@ -89,8 +90,9 @@ extern "C" int hsr_make_hist_segments_device(const void *dData, size_t size, siz
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const uint64_t segments = (size + segmentBytes - 1) / segmentBytes;
-  const unsigned grid = (unsigned)(segments < (uint64_t)sms * 8 ? segments : (uint64_t)sms * 8);
-  segments_kernel<<<grid, kHistThreads, 0, static_cast<cudaStream_t>(cudaStream)>>>(static_cast<const uint8_t *>(dData), size, segmentBytes,
+  const uint64_t ctas = (segments + kSegWarps - 1) / kSegWarps;
+  const unsigned grid = (unsigned)(ctas < (uint64_t)sms * 16 ? ctas : (uint64_t)sms * 16);
+  segments_kernel<<<grid, kSegWarps * 32, 0, static_cast<cudaStream_t>(cudaStream)>>>(static_cast<const uint8_t *>(dData), size, segmentBytes,
                                                                                 bits, dSymbolCounts);
   return cudaGetLastError() == cudaSuccess ? 1 : -2;
 }

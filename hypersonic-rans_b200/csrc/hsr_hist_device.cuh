@@ -125,4 +125,82 @@ __device__ inline void cta_normalize(const uint32_t *sHist, uint64_t dataBytes, 
   __syncthreads();
 }
 
+
+// ---- one WARP per segment: the order-dependent part of normalize_hist runs on one lane whatever the CTA size, so
+// many short segments (per-block histograms) are best served by as many concurrent warps as the SM holds.
+
+// counts bytes [begin, end) into the warp's private histogram h[256] (shared memory, zeroed here)
+__device__ inline void warp_observe(const uint8_t *data, uint64_t begin, uint64_t end, uint32_t *h, uint32_t lane)
+{
+  for (int k = lane; k < 256; k += 32) h[k] = 0;
+  __syncwarp();
+  const uint8_t *p = data + begin;
+  const uint64_t len = end - begin;
+  uint64_t head = (16u - (reinterpret_cast<uintptr_t>(p) & 15u)) & 15u;
+  if (head > len) head = len;
+  if (lane < head) atomicAdd(h + p[lane], 1u);
+  const uint4 *v = reinterpret_cast<const uint4 *>(p + head);
+  const uint64_t vecs = (len - head) / 16;
+  for (uint64_t i = lane; i < vecs; i += 32) {
+    const uint4 q = __ldg(v + i);
+    count4(h, q.x); count4(h, q.y); count4(h, q.z); count4(h, q.w);
+  }
+  const uint64_t done = head + vecs * 16;
+  if (lane < len - done) atomicAdd(h + p[done + lane], 1u);
+  __syncwarp();
+}
+
+// normalize_hist (src/hist.cpp:16-215) by one warp: lanes scale, lane 0 runs the sort and the steal/charity loops
+__device__ inline void warp_normalize(const uint32_t *h, uint64_t dataBytes, int bits, uint16_t *capped, uint8_t *idx, uint16_t *outCount,
+                                      uint32_t lane)
+{
+  const uint32_t total = 1u << bits;
+  const float mul = __fdiv_rn((float)total, __ull2float_rn(dataBytes));
+  uint32_t part = 0;
+  for (int i = lane; i < 256; i += 32) {
+    const float scaled = __fadd_rn(__fmul_rn(__uint2float_rn(h[i]), mul), 0.5f);
+    uint16_t c = (uint16_t)__float2uint_rz(scaled);
+    if (c == 0 && h[i]) c = 1;
+    capped[i] = c;
+    idx[i] = (uint8_t)i;
+    part += c;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+  __syncwarp();
+  if (lane == 0 && part != total) {
+    uint32_t sum = part;
+    for (int i = 256 / 2 - 1; i >= 0; i--) heapify(idx, capped, 256, i);
+    for (int i = 255; i >= 0; i--) {
+      const uint8_t t = idx[0]; idx[0] = idx[i]; idx[i] = t;
+      heapify(idx, capped, i, 0);
+    }
+    int minTwo = 0;
+    for (int i = 0; i < 256; i++)
+      if (capped[idx[i]] >= 2) { minTwo = i; break; }
+    bool ready = false;
+    while (!ready && sum > total) {
+      for (int i = minTwo; i < 256; i++) {
+        capped[idx[i]]--; sum--;
+        if (sum == total) { ready = true; break; }
+      }
+      if (ready) break;
+      for (int i = minTwo; i < 256; i++)
+        if (capped[idx[i]] >= 2) { minTwo = i; break; }
+    }
+    while (!ready && sum < total) {
+      for (int i = 255; i >= minTwo; i--) {
+        capped[idx[i]]++; sum++;
+        if (sum == total) { ready = true; break; }
+      }
+      if (ready) break;
+      for (int i = minTwo; i < 256; i++)
+        if (capped[idx[i]] >= 2) { minTwo = i; break; }
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < 256; i += 32) outCount[i] = capped[i];
+  __syncwarp();
+}
+
 } // namespace hsr
