@@ -269,3 +269,28 @@ def test_full_size_100mb_round_trip(gpu):
         n_out, out = gpu.decode(fam, states, bits, stream, n)
         assert n_out == n, gpu.last_error()
         assert np.array_equal(out[:n], data), (fam, states, bits)
+
+
+def test_corrupted_streams_never_crash_or_overrun(gpu, golden):
+    """Random byte flips anywhere in a stream: the call must return 0 or n, never write past n, and leave the
+    device healthy (the reference has undefined behaviour here; ours is bounded by the host-validated index and by
+    the clamped word ring)."""
+    rng = np.random.default_rng(12345)
+    cases = [("multi", ck.MT, 64, 15), ("multi", ck.MT, 32, 12), ("multi", ck.BLOCK, 32, 10), ("multi", ck.BLOCK, 64, 13),
+             ("multi", ck.RAW, 64, 12), ("runs", ck.MT, 64, 11), ("runs", ck.BLOCK, 64, 15)]
+    for name, fam, states, bits in cases:
+        good = golden[f"stream/{name}/{fam}/{states}/{bits}"]
+        data = golden[f"in/{name}"]
+        n = data.size
+        for trial in range(12):
+            bad = good.copy()
+            flips = int(rng.integers(1, 6))
+            # bias the flips towards the headers, where the framing lives
+            for _ in range(flips):
+                pos = int(rng.integers(0, min(bad.size, 2048))) if rng.random() < 0.6 else int(rng.integers(0, bad.size))
+                bad[pos] ^= np.uint8(1 << int(rng.integers(0, 8)))
+            out = np.full(n + 256, 0xCC, np.uint8)
+            got, _ = gpu.decode(fam, states, bits, bad, n, out=out)
+            assert got <= n, (name, fam, states, bits, trial, got)  # a flipped length field may legitimately shorten it
+            assert np.all(out[n:] == 0xCC), "wrote past the decoded length"
+        _check(gpu, fam, states, bits, good, data, "after fuzz")
