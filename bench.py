@@ -56,7 +56,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-only", action="store_true", help="skip e2e / index / CPU legs (profiling runs)")
     ap.add_argument("--table", type=int, default=0, help="hsr_set_option table: 0 auto, 1 bitmap-rank, 2 packed")
-    ap.add_argument("--extra", action="store_true", help="also report BASELINE configs 2 and 3 (single-recurrence codecs)")
+    ap.add_argument("--ctas-per-sm", type=int, default=0, help="cap resident one-warp CTAs per SM (occupancy experiments)")
+    ap.add_argument("--extra", action="store_true", help="also measure batch decode, the device encoder and the histogram kernels")
     return ap.parse_args()
 
 
@@ -204,8 +205,9 @@ def run_reference(a, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def single_recurrence_extras(pkg, torch, a):
-    """BASELINE configs 2 and 3: one stream = one warp; latency-bound by construction (SURVEY.md finding 1)."""
+def other_configs(pkg, torch, a, heavy):
+    """BASELINE configs 1-3 (single-recurrence codecs: one stream = one warp, latency-bound by construction, SURVEY.md
+    finding 1); with `heavy` also the batch, device-encoder and histogram measurements."""
     import checkers as ck
     res = {}
     n = 100_000_000
@@ -232,6 +234,8 @@ def single_recurrence_extras(pkg, torch, a):
         res[label] = {"gpu_decoded_GBps": round(n / ms / 1e6, 4), "gpu_ms": round(ms, 3), "bit_exact": ok,
                       "cpu_avx2_1thread_GBps": round(n / cpu_s / 1e9, 4), "streams": 1, "warps": 1}
         ps.free()
+    if not heavy:
+        return res
 
     # the same two codecs with many independent streams in one launch (hsr_stream_upload_batch): one warp per stream
     k_streams, each = 2368, 400_000
@@ -330,6 +334,16 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (" + pkg.last_error() + ")")
     torch.cuda.set_device(local_rank)
     pkg.lib().hsr_set_device(local_rank)
+    affinity = "unchanged"
+    if world > 1:
+        # keep this rank's host threads (and therefore its pinned buffers) on the CPUs next to its GPU
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            affinity = f"nvml ({len(os.sched_getaffinity(0))} cpus)"
+        except Exception as exc:  # not fatal: VMs often hide the topology
+            affinity = f"unavailable ({type(exc).__name__})"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -353,6 +367,7 @@ def main():
         return float(t.item())
 
     pkg.set_option("table", a.table)
+    pkg.set_option("warps", a.ctas_per_sm)
     data, stream, enc_s = make_input(pkg, a, rank)
     n = data.size
     comp = stream.size
@@ -386,7 +401,7 @@ def main():
     if a.kernel_only:
         if rank == 0:
             print(json.dumps({"kernel_only": True, "value": round(value, 3), "unit": "GB/s", "ms_per_step": round(ms_per_step, 4),
-                              "bits": a.bits, "states": a.states, "table": a.table, "blocks": int(units), "compressed": comp,
+                              "bits": a.bits, "states": a.states, "table": a.table, "ctas_per_sm": a.ctas_per_sm, "blocks": int(units), "compressed": comp,
                               "traffic_GBps": round((comp + n) / (ms_per_step * 1e-3) / 1e9, 1), "clocks": clocks}), flush=True)
         return
 
@@ -450,7 +465,7 @@ def main():
                        "blocks_total": int(units_total), "compressed_bytes_total": int(comp_total),
                        "stream_producer": "reference mt_ encoder (oracle/_ref), unmodified",
                        "l2_policy": "inputs larger than L2: 1.78 GB touched per step vs 126 MB L2",
-                       "parallelism": f"{world} x contiguous block range, no collective",
+                       "parallelism": f"{world} x contiguous block range, no collective", "cpu_affinity": affinity,
                        "table": "auto (bitmap-rank for bits>=13, packed slot table below)"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "peak_source": peak_src, "kernel": f"units_n{a.states}_b{a.bits}_t{2 if (a.bits <= 12 and a.table != 1) else 1}",
@@ -465,8 +480,7 @@ def main():
         }
         if not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a, stream, n)
-        if a.extra:
-            line["single_recurrence"] = single_recurrence_extras(pkg, torch, a)
+        line["other_configs"] = other_configs(pkg, torch, a, a.extra)
         print(json.dumps(line), flush=True)
     ps.free()
     hin.free(); hout.free()

@@ -73,7 +73,7 @@ extern "C" int hsr_set_option(const char *key, long value)
 {
   if (!key) return -1;
   if (!strcmp(key, "table")) { if (value < 0 || value > 2) return -1; g_optTable = value; return 0; }
-  if (!strcmp(key, "warps")) { if (value < 0 || value > 16) return -1; g_optWarps = value; return 0; }
+  if (!strcmp(key, "warps")) { if (value < 0 || value > 32) return -1; g_optWarps = value; return 0; }
   if (!strcmp(key, "chunk_mb")) { if (value < 0) return -1; g_optChunkMb = value; return 0; }
   return -1;
 }

@@ -41,7 +41,7 @@ int hsr_device_count(void);
 const char *hsr_last_error(void);
 /* Tuning knobs, for benchmarking variants without rebuilding. Unknown keys return -1.
  *   "table"      0 = auto (packed slot table for bits <= 12, bitmap-rank table above), 1 = bitmap-rank, 2 = packed
- *   "warps"      warps per CTA for the mt_ kernel (1..16, 0 = auto)
+ *   "warps"      cap on resident one-warp CTAs per SM for the mt_ kernel (1..32, 0 = as many as fit; experiments)
  *   "chunk_mb"   host pipeline chunk size in MiB for hsr_decode on mt_ streams (0 = auto)                      */
 int hsr_set_option(const char *key, long value);
 long hsr_get_option(const char *key);

@@ -107,3 +107,17 @@ def test_full_size_100mb(gpu):
     if ck.have_ref():
         rn, ro = ck.ref_decode(ck.MT, 64, 15, stream, n, ck.IMPL_POOL)
         assert rn == n and np.array_equal(ro[:n], data)
+
+
+def test_full_size_1gb_config4(gpu):
+    """BASELINE config 4 size: 1,000,000,000 bytes through the device encoder and the CUDA decoder; the reference's
+    thread-pool decoder must agree on the same stream."""
+    n = 1_000_000_000
+    data = gpu.synth_zipf(n, 1.0, seed=42, segment_bytes=65536)
+    stream = gpu.encode_mt(64, 15, data)
+    got_n, got = gpu.decode(ck.MT, 64, 15, stream, n)
+    assert got_n == n and np.array_equal(got[:n], data)
+    del got
+    if ck.have_ref():
+        rn, ro = ck.ref_decode(ck.MT, 64, 15, stream, n, ck.IMPL_POOL)
+        assert rn == n and np.array_equal(ro[:n], data)
