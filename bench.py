@@ -335,6 +335,7 @@ def main():
     torch.cuda.set_device(local_rank)
     pkg.lib().hsr_set_device(local_rank)
     affinity = "unchanged"
+    all_cpus = os.sched_getaffinity(0)
     if world > 1:
         # keep this rank's host threads (and therefore its pinned buffers) on the CPUs next to its GPU
         try:
@@ -478,6 +479,7 @@ def main():
             "index_ms": {"host_walk": round(index_host_ms, 3), "device_walk": round(index_device_ms, 3)},
             "setup_s": {"reference_encode": round(enc_s, 2)},
         }
+        os.sched_setaffinity(0, all_cpus)  # the CPU baseline may use every host core
         if not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a, stream, n)
         line["other_configs"] = other_configs(pkg, torch, a, a.extra)

@@ -47,7 +47,10 @@ static void set_err(const char *fmt, ...)
     }                                                                                                     \
   } while (0)
 
-static std::atomic<long> g_optTable{0}, g_optWarps{0}, g_optChunkMb{0};
+static std::atomic<long> g_optTable{0}, g_optWarps{0}, g_optChunkMb{0}, g_optIndex{0};
+
+// hsr_index.cu
+bool hsr_parallel_mt_index(const uint8_t *dIn, uint64_t compLen, uint64_t n, int N, int bits, std::vector<hsr_block_t> *out, float *ms);
 
 extern "C" int hsr_version(void) { return HSR_VERSION; }
 
@@ -75,6 +78,7 @@ extern "C" int hsr_set_option(const char *key, long value)
   if (!strcmp(key, "table")) { if (value < 0 || value > 2) return -1; g_optTable = value; return 0; }
   if (!strcmp(key, "warps")) { if (value < 0 || value > 32) return -1; g_optWarps = value; return 0; }
   if (!strcmp(key, "chunk_mb")) { if (value < 0) return -1; g_optChunkMb = value; return 0; }
+  if (!strcmp(key, "index")) { if (value < 0 || value > 2) return -1; g_optIndex = value; return 0; }
   return -1;
 }
 
@@ -84,6 +88,7 @@ extern "C" long hsr_get_option(const char *key)
   if (!strcmp(key, "table")) return g_optTable;
   if (!strcmp(key, "warps")) return g_optWarps;
   if (!strcmp(key, "chunk_mb")) return g_optChunkMb;
+  if (!strcmp(key, "index")) return g_optIndex;
   return -1;
 }
 
@@ -573,6 +578,15 @@ extern "C" hsr_stream_t *hsr_stream_from_device(int family, int N, int bits, con
     if (h.compLen > kMaxUnitIn) { set_err("raw streams above 4 GiB compressed are not supported"); return nullptr; }
     s->blocks.push_back(raw_unit(N, h));
   } else if (family == HSR_MT) {
+    // segment-parallel index first (hsr_index.cu); the serial walk below is the fallback and the error reporter
+    const long indexMode = g_optIndex;
+    float parallelMs = 0;
+    if (indexMode != 1 && hsr_parallel_mt_index(dIn, h.compLen, h.n, N, bits, &s->blocks, &parallelMs)) {
+      s->indexMs = parallelMs;
+      if (!stream_finish(s.get())) return nullptr;
+      return s.release();
+    }
+    if (indexMode == 2) { set_err("parallel index declined this stream"); return nullptr; }
     unsigned long long *dRes = nullptr;
     CU_TRY(cudaMalloc(&dRes, 16), return nullptr);
     uint64_t cap = std::max<uint64_t>(1024, h.n / 32768 + 64);

@@ -42,7 +42,9 @@ const char *hsr_last_error(void);
 /* Tuning knobs, for benchmarking variants without rebuilding. Unknown keys return -1.
  *   "table"      0 = auto (packed slot table for bits <= 12, bitmap-rank table above), 1 = bitmap-rank, 2 = packed
  *   "warps"      cap on resident one-warp CTAs per SM for the mt_ kernel (1..32, 0 = as many as fit; experiments)
- *   "chunk_mb"   host pipeline chunk size in MiB for hsr_decode on mt_ streams (0 = auto)                      */
+ *   "chunk_mb"   host pipeline chunk size in MiB for hsr_decode on mt_ streams (0 = auto)
+ *   "index"      block index of device-resident mt_ streams: 0 = segment-parallel with serial fallback,
+ *                1 = serial walk only, 2 = segment-parallel only (fail instead of falling back; tests)         */
 int hsr_set_option(const char *key, long value);
 long hsr_get_option(const char *key);
 
@@ -126,7 +128,8 @@ typedef struct hsr_stream hsr_stream_t;
 hsr_stream_t *hsr_stream_upload(int family, int stateCount, int bits, const uint8_t *pInData, size_t inLength, int shard,
                                 int shards);
 /* Wrap compressed bytes that already live in device memory (16-byte aligned, readable up to inLength).
- * mt_: the header chain is walked by a device kernel (serial; see hsr_stream_index_ms). */
+ * mt_: the block index is built on the device — K warps each find the first header of their stream segment and
+ * walk the chain from there, handing over where they meet (hsr_index.cu); see hsr_stream_index_ms. */
 hsr_stream_t *hsr_stream_from_device(int family, int stateCount, int bits, const void *dIn, size_t inLength);
 /* A batch of independent streams of one codec (see hsr_decode_batch) made resident for repeated decoding. Offsets in
  * `items` are relative to inBase; the decode writes stream i at dOut + items[i].outOffset, so dOut must hold

@@ -294,3 +294,61 @@ def test_corrupted_streams_never_crash_or_overrun(gpu, golden):
             assert got <= n, (name, fam, states, bits, trial, got)  # a flipped length field may legitimately shorten it
             assert np.all(out[n:] == 0xCC), "wrote past the decoded length"
         _check(gpu, fam, states, bits, good, data, "after fuzz")
+
+
+def _index_tuple(b):
+    return (b.inOffset, b.inEnd, b.outOffset, b.count, b.kind, b.symbol, b.tail)
+
+
+def test_parallel_device_index_equals_host_walk(gpu, golden):
+    """hsr_index.cu: K warps find headers by signature and walk their segments; the result must be the serial walk's."""
+    import torch
+    streams = [(golden["stream/multi/2/64/15"], 64, 15), (golden["stream/multi/2/32/12"], 32, 12),
+               (golden["stream/runs/2/64/11"], 64, 11), (golden["stream/runs/2/32/14"], 32, 14),
+               (golden["stream/small/2/64/10"], 64, 10), (golden["stream/tiny65/2/32/13"], 32, 13)]
+    big = gpu.synth_zipf(40_000_003, 1.0, seed=3, segment_bytes=65536)
+    big[5_000_000:9_000_000] = 0x20   # a long single-symbol run in the middle of a many-segment stream
+    if ck.have_ref():
+        streams.append((ck.ref_encode(ck.MT, 64, 15, big), 64, 15))
+        streams.append((ck.ref_encode(ck.MT, 32, 10, big[:20_000_001]), 32, 10))
+    streams.append((gpu.encode_mt(64, 13, big), 64, 13))
+    streams.append((gpu.encode_mt(32, 15, big, 32768), 32, 15))
+    for stream, states, bits in streams:
+        host = [_index_tuple(b) for b in gpu.mt_index(states, stream)]
+        dev_in = torch.from_numpy(stream.copy()).cuda()
+        for mode in (2, 1):  # parallel only, then the serial walk
+            gpu.set_option("index", mode)
+            try:
+                if mode == 2 and stream.size < 16 + 2 * (16 + 4 * states + 512):
+                    continue  # too short for the segment scheme: auto mode falls back
+                ds = gpu.PreparedStream.from_device(ck.MT, states, bits, dev_in.data_ptr(), stream.size)
+                assert [_index_tuple(b) for b in ds.index()] == host, (states, bits, mode, stream.size)
+                ds.free()
+            finally:
+                gpu.set_option("index", 0)
+        # auto mode must always work and decode
+        n = int(np.frombuffer(stream[:8].tobytes(), np.uint64)[0])
+        ds = gpu.PreparedStream.from_device(ck.MT, states, bits, dev_in.data_ptr(), stream.size)
+        out = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
+        ds.decode_async(out.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert ds.status() == 0
+        ds.free()
+    # corrupted chains: the parallel path must decline or agree, never invent an index
+    rng = np.random.default_rng(5)
+    base, states, bits = streams[0]
+    for trial in range(20):
+        bad = base.copy()
+        bad[int(rng.integers(16, bad.size))] ^= np.uint8(1 << int(rng.integers(0, 8)))
+        dev_in = torch.from_numpy(bad).cuda()
+        try:
+            host = [_index_tuple(b) for b in gpu.mt_index(states, bad)]
+        except gpu.HsrError:
+            host = None
+        try:
+            ds = gpu.PreparedStream.from_device(ck.MT, states, bits, dev_in.data_ptr(), bad.size)
+            got = [_index_tuple(b) for b in ds.index()]
+            ds.free()
+        except gpu.HsrError:
+            got = None
+        assert got == host, trial
