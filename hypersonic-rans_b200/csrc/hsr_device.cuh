@@ -81,6 +81,22 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int Pending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(Pending) : "memory"); }
 
+// mbarrier + TMA bulk copy (cp.async.bulk -> UBLKCP): one elected lane moves a whole ring segment
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 __device__ __forceinline__ void st_global_u8(uint8_t *p, uint32_t v) { asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------- layout
@@ -110,7 +126,8 @@ struct WarpLayout {
   static constexpr int kOffSym = kOffEnt + kEntBytes;
   static constexpr int kOffPacked = kOffSym + kSymBytes;
   static constexpr int kOffRing = kOffPacked + kPackedBytes;
-  static constexpr int kBytes = kOffRing + kRingBytes; // per warp (= per CTA), multiple of 16
+  static constexpr int kOffBar = kOffRing + kRingBytes;   // one mbarrier per ring buffer (TMA bulk copies)
+  static constexpr int kBytes = kOffBar + 32;             // per warp (= per CTA), multiple of 16
   static_assert(kBytes % 16 == 0 && kBytes <= 48 * 1024, "static shared memory budget");
 };
 
@@ -177,6 +194,122 @@ struct WordRing {
 
   __device__ __forceinline__ void drain() const { cp_async_wait<0>(); }
 };
+
+// The same ring fed by the TMA: a full segment is one cp.async.bulk (UBLKCP) issued by lane 0 and tracked by an
+// mbarrier per buffer; only the last, partial segment of a block still goes through the clamped, zero-filling
+// LDGSTS path above so that nothing past the block's end is ever read. Segments are numbered globally across the
+// blocks a warp decodes (buffer = g % kBufs, barrier phase parity = (g / kBufs) & 1), and a new block first waits
+// for whatever the previous one left in flight, so a barrier is never re-armed before its phase completed.
+template <class L>
+struct WordRingTma {
+  uint32_t sbuf, sbar;
+  const uint8_t *gbase;
+  uint32_t glimit;
+  uint32_t seg;      // current segment of this block
+  uint32_t g0;       // global number of this block's segment 0
+  uint32_t gIssued;  // next global segment number to issue
+  uint32_t gWaited;  // every global segment below this has been waited for
+  uint32_t wp, wlimit;
+  uint32_t stuck;    // set if a barrier never completed (reported, never hangs)
+
+  __device__ __forceinline__ uint32_t buf(uint32_t g) const { return sbuf + (g % L::kBufs) * L::kSeg; }
+  __device__ __forceinline__ uint32_t bar(uint32_t g) const { return sbar + (g % L::kBufs) * 8u; }
+
+  __device__ __forceinline__ void init(uint32_t sbuf_, uint32_t sbar_, uint32_t lane)
+  {
+    sbuf = sbuf_; sbar = sbar_;
+    gIssued = gWaited = 0; stuck = 0;
+    if (lane == 0) {
+#pragma unroll
+      for (uint32_t b = 0; b < (uint32_t)L::kBufs; b++) mbar_init(sbar + b * 8u, 1u);
+      fence_mbar_init();
+    }
+    __syncwarp();
+  }
+
+  __device__ __forceinline__ void issue(uint32_t lane)
+  {
+    const uint32_t g = gIssued++;
+    const uint32_t srcOff = (g - g0) * L::kStride;
+    if (srcOff + (uint32_t)L::kSeg <= glimit) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar(g), (uint32_t)L::kSeg);
+        bulk_copy_g2s(buf(g), gbase + srcOff, (uint32_t)L::kSeg, bar(g));
+      }
+    } else { // partial or empty segment at the end of the block: clamped 16-byte copies, zero fill beyond the limit
+      const uint32_t off = srcOff + lane * 16u;
+      uint32_t bytes = off < glimit ? glimit - off : 0u;
+      bytes = bytes > 16u ? 16u : bytes;
+      cp_async16(buf(g) + lane * 16u, gbase + (bytes ? off : 0u), bytes);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(g));
+    }
+  }
+
+  __device__ __forceinline__ void wait_next()
+  {
+    const uint32_t g = gWaited++;
+    const uint32_t b = bar(g), parity = (g / L::kBufs) & 1u;
+    uint32_t spins = 0;
+    while (!mbar_try_wait(b, parity)) {
+      if (++spins > (1u << 22)) { stuck = 1; break; }
+    }
+  }
+
+  __device__ __forceinline__ void start(const uint8_t *firstWord, const uint8_t *streamEnd, uint32_t lane)
+  {
+    while (gWaited < gIssued) wait_next(); // segments the previous block prefetched and never used
+    __syncwarp();                          // every lane is done with whatever lived in the ring before
+    const uintptr_t a = reinterpret_cast<uintptr_t>(firstWord);
+    gbase = reinterpret_cast<const uint8_t *>(a & ~(uintptr_t)15);
+    const uint64_t avail = (uint64_t)(streamEnd - gbase);
+    glimit = avail > 0xffffffffull ? 0xffffffffu : (uint32_t)avail;
+    seg = 0;
+    g0 = gIssued;
+#pragma unroll
+    for (uint32_t k = 0; k + 2 <= (uint32_t)L::kBufs; k++)
+      issue(lane);
+    wait_next();
+    wp = buf(g0) + (uint32_t)(a & 15);
+    wlimit = buf(g0) + L::kStride;
+  }
+
+  __device__ __forceinline__ void advance_if_needed(uint32_t lane)
+  {
+    if (wp >= wlimit) {
+      const uint32_t into = wp - wlimit;
+      seg += 1;
+      issue(lane);  // segment seg + kBufs - 2 lands in the buffer of segment seg - 2, abandoned one segment ago
+      wait_next();  // segment seg
+      const uint32_t b = buf(g0 + seg);
+      wp = b + into;
+      wlimit = b + L::kStride;
+    }
+  }
+
+  __device__ __forceinline__ uint32_t cursor() const { return seg * L::kStride + (wp - buf(g0 + seg)); }
+
+  __device__ __forceinline__ void drain()
+  {
+    while (gWaited < gIssued) wait_next();
+  }
+};
+
+// Measured on B200 (profiles/r1/sweep_tma_ring_experiment.jsonl): the TMA ring is correct (all parity tests pass) but
+// 26-31 % SLOWER than the LDGSTS ring (571 vs 773 GB/s at mt_64x15, 838 vs 1220 at 10 bits): a 512-byte segment is
+// too small to amortise the mbarrier try_wait round trip per segment, and the extra live state costs registers
+// (92 in the packed 10-bit kernel). It stays available for larger-segment experiments; LDGSTS is the default.
+#ifndef HSR_RING_TMA
+#define HSR_RING_TMA 0
+#endif
+template <class L>
+#if HSR_RING_TMA
+using Ring = WordRingTma<L>;
+#else
+using Ring = WordRing<L>;
+#endif
 
 // ---------------------------------------------------------------------------------------------- table build
 
@@ -359,7 +492,7 @@ struct Decoder {
 
   // mode 0: packed table, 1: rank table with all symbols present, 2: rank table with the rank->symbol map
   template <int kMode>
-  __device__ __forceinline__ void rows_impl(uint32_t &x0, uint32_t &x1, WordRing<L> &ring, uint8_t *outLane, uint32_t rows,
+  __device__ __forceinline__ void rows_impl(uint32_t &x0, uint32_t &x1, Ring<L> &ring, uint8_t *outLane, uint32_t rows,
                                             uint32_t lane, uint32_t ltMask) const
   {
     for (uint32_t r = 0; r < rows; r++) {
@@ -384,7 +517,7 @@ struct Decoder {
     }
   }
 
-  __device__ __forceinline__ void rows(const TableInfo &info, uint32_t &x0, uint32_t &x1, WordRing<L> &ring, uint8_t *outLane,
+  __device__ __forceinline__ void rows(const TableInfo &info, uint32_t &x0, uint32_t &x1, Ring<L> &ring, uint8_t *outLane,
                                        uint64_t nrows, uint32_t lane, uint32_t ltMask) const
   {
     while (nrows) { // 64-bit row counts are split so the hot loop keeps a 32-bit counter
@@ -401,7 +534,7 @@ struct Decoder {
   }
 
   // the < N leftover symbols (src/rANS32x32_16w.cpp:238-266): lanes whose byte position is inside the buffer
-  __device__ __forceinline__ void tail(uint32_t &x0, uint32_t &x1, WordRing<L> &ring, uint8_t *outLane, uint32_t lanePos,
+  __device__ __forceinline__ void tail(uint32_t &x0, uint32_t &x1, Ring<L> &ring, uint8_t *outLane, uint32_t lanePos,
                                        uint32_t left, uint32_t lane, uint32_t ltMask) const
   {
     ring.advance_if_needed(lane);

@@ -58,6 +58,10 @@ __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
 
   Decoder<BITS, N, TK> dec;
   dec.init(sw);
+  Ring<L> ring;
+#if HSR_RING_TMA
+  ring.init(sw + L::kOffRing, sw + L::kOffBar, lane);
+#endif
 
   for (;;) {
     uint32_t b = 0;
@@ -99,8 +103,11 @@ __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
     if constexpr (N == 64)
       x1 = ldg_u32_a2(statesPtr + 4 * (lane + 32));
 
-    WordRing<L> ring;
+#if HSR_RING_TMA
+    ring.start(words, end, lane);
+#else
     ring.start(sw + L::kOffRing, words, end, lane);
+#endif
 
     const uint64_t rows = (count - tailCount) / N;
     uint8_t *outLane = out + lanePos;
@@ -110,6 +117,10 @@ __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
     ring.drain();
     if (ring.cursor() > ring.glimit)
       raise(p.counter, p.streamStatus, streamId, HSR_ERR_OVERRUN, lane);
+#if HSR_RING_TMA
+    if (ring.stuck)
+      raise(p.counter, p.streamStatus, streamId, HSR_ERR_INTERNAL, lane);
+#endif
   }
 }
 
@@ -120,7 +131,7 @@ __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
 // has been decoded. One warp walks the whole stream, rebuilding its tables between sections.
 template <int BITS, int N, int TK>
 __device__ __forceinline__ void block_stream_decode(const BlockStreamParams &p, const BlockStreamDesc &d, uint32_t streamId, uint32_t sw,
-                                                    uint32_t lane, uint32_t ltMask, uint32_t lanePos)
+                                                    uint32_t lane, uint32_t ltMask, uint32_t lanePos, Ring<WarpLayout<BITS, N, TK>> &ring)
 {
   using L = WarpLayout<BITS, N, TK>;
 
@@ -142,7 +153,6 @@ __device__ __forceinline__ void block_stream_decode(const BlockStreamParams &p, 
   const uint64_t outLengthInStates = n - N + 1;
   uint64_t i = 0;
   bool haveHist = false;
-  WordRing<L> ring;
   const uint32_t sRing = sw + L::kOffRing;
 
   do {
@@ -182,7 +192,11 @@ __device__ __forceinline__ void block_stream_decode(const BlockStreamParams &p, 
         return;
       }
       const uint64_t rows = blockEnd > i ? (blockEnd - i + N - 1) / N : 0;
+#if HSR_RING_TMA
+      ring.start(in + pos, streamEnd, lane);
+#else
       ring.start(sRing, in + pos, streamEnd, lane);
+#endif
       dec.rows(info, x0, x1, ring, outBase + i + lanePos, rows, lane, ltMask);
       ring.drain();
       if (ring.cursor() > ring.glimit) {
@@ -204,7 +218,11 @@ __device__ __forceinline__ void block_stream_decode(const BlockStreamParams &p, 
       raise(p.counter, p.streamStatus, streamId, HSR_ERR_HIST, lane);
       return;
     }
+#if HSR_RING_TMA
+    ring.start(in + pos, streamEnd, lane);
+#else
     ring.start(sRing, in + pos, streamEnd, lane);
+#endif
     dec.tail(x0, x1, ring, outBase + i + lanePos, lanePos, (uint32_t)(n - i), lane, ltMask);
     ring.drain();
   }
@@ -218,8 +236,12 @@ __device__ __forceinline__ void block_kernel_body(const BlockStreamParams &p)
   const uint32_t lane = lane_id();
   const uint32_t ltMask = lanemask_lt();
   const uint32_t lanePos = idx2idx_lane(lane);
+  Ring<L> ring;
+#if HSR_RING_TMA
+  ring.init(sw + L::kOffRing, sw + L::kOffBar, lane);
+#endif
   if (p.streams == nullptr) {
-    block_stream_decode<BITS, N, TK>(p, p.single, 0u, sw, lane, ltMask, lanePos);
+    block_stream_decode<BITS, N, TK>(p, p.single, 0u, sw, lane, ltMask, lanePos, ring);
     return;
   }
   for (;;) { // persistent: streams are handed out by an atomic counter
@@ -234,7 +256,7 @@ __device__ __forceinline__ void block_kernel_body(const BlockStreamParams &p)
     d.inLength = __ldg(&p.streams[s].inLength);
     d.outOffset = __ldg(&p.streams[s].outOffset);
     d.n = __ldg(&p.streams[s].n);
-    block_stream_decode<BITS, N, TK>(p, d, s, sw, lane, ltMask, lanePos);
+    block_stream_decode<BITS, N, TK>(p, d, s, sw, lane, ltMask, lanePos, ring);
   }
 }
 

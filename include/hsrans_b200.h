@@ -157,6 +157,7 @@ int hsr_stream_decode_async(hsr_stream_t *s, void *dOut, size_t outCapacity, uns
 #define HSR_ERR_OVERRUN 2u  /* the word cursor ran past the block / stream end */
 #define HSR_ERR_ALIGN 4u    /* block end not a multiple of the state count (src/block_rANS32x32_16w_decode.cpp:82-83) */
 #define HSR_ERR_BOUNDS 8u   /* a block would write past the decoded length */
+#define HSR_ERR_INTERNAL 16u /* a staging barrier never completed (should not happen; reported instead of hanging) */
 unsigned hsr_stream_status(hsr_stream_t *s);
 
 /* ------------------------------------------------------------------------------------------------ histogram */
