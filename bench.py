@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--kernel-only", action="store_true", help="skip e2e / index / CPU legs (profiling runs)")
     ap.add_argument("--table", type=int, default=0, help="hsr_set_option table: 0 auto, 1 bitmap-rank, 2 packed")
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="cap resident one-warp CTAs per SM (occupancy experiments)")
+    ap.add_argument("--headline-only", action="store_true", help="skip the configs 1-3 leg (profiling runs: only the headline kernel launches)")
     ap.add_argument("--extra", action="store_true", help="also measure batch decode, the device encoder and the histogram kernels")
     return ap.parse_args()
 
@@ -482,7 +483,8 @@ def main():
         os.sched_setaffinity(0, all_cpus)  # the CPU baseline may use every host core
         if not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a, stream, n)
-        line["other_configs"] = other_configs(pkg, torch, a, a.extra)
+        if not a.headline_only:
+            line["other_configs"] = other_configs(pkg, torch, a, a.extra)
         print(json.dumps(line), flush=True)
     ps.free()
     hin.free(); hout.free()

@@ -54,12 +54,11 @@ __global__ void __launch_bounds__(kSegWarps * 32) enc_hist_kernel(const uint8_t 
 {
   __shared__ uint32_t sHist[kSegWarps][256];
   __shared__ uint16_t sCapped[kSegWarps][256];
-  __shared__ uint8_t sIdx[kSegWarps][256];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   for (uint32_t k = blockIdx.x * kSegWarps + warp; k < pl.numBlocks; k += gridDim.x * kSegWarps) {
     const uint64_t begin = block_begin(pl, k), end = block_end(pl, k);
     warp_observe(data, begin, end, sHist[warp], lane);
-    warp_normalize(sHist[warp], end - begin, bits, sCapped[warp], sIdx[warp], counts + (uint64_t)k * 256, lane); // :209-210
+    warp_normalize(sHist[warp], end - begin, bits, sCapped[warp], sHist[warp], counts + (uint64_t)k * 256, lane); // :209-210
   }
 }
 

@@ -43,14 +43,13 @@ __global__ void __launch_bounds__(kSegWarps * 32) segments_kernel(const uint8_t 
 {
   __shared__ uint32_t sHist[kSegWarps][256];
   __shared__ uint16_t sCapped[kSegWarps][256];
-  __shared__ uint8_t sIdx[kSegWarps][256];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint64_t segments = (size + segmentBytes - 1) / segmentBytes;
   for (uint64_t seg = (uint64_t)blockIdx.x * kSegWarps + warp; seg < segments; seg += (uint64_t)gridDim.x * kSegWarps) {
     const uint64_t begin = seg * segmentBytes;
     const uint64_t end = begin + segmentBytes < size ? begin + segmentBytes : size;
     warp_observe(data, begin, end, sHist[warp], lane);
-    warp_normalize(sHist[warp], end - begin, bits, sCapped[warp], sIdx[warp], symbolCounts + seg * 256, lane);
+    warp_normalize(sHist[warp], end - begin, bits, sCapped[warp], sHist[warp], symbolCounts + seg * 256, lane);
   }
 }
 

@@ -150,52 +150,89 @@ __device__ inline void warp_observe(const uint8_t *data, uint64_t begin, uint64_
   __syncwarp();
 }
 
-// normalize_hist (src/hist.cpp:16-215) by one warp: lanes scale, lane 0 runs the sort and the steal/charity loops
-__device__ inline void warp_normalize(const uint32_t *h, uint64_t dataBytes, int bits, uint16_t *capped, uint8_t *idx, uint16_t *outCount,
+// heapify of src/hist.cpp:112-129 on packed heap slots: slot = capped value << 8 | symbol index, so one shared-memory
+// load per child replaces the reference's pVal[pIdx[child]] double indirection. Comparisons use the value only
+// (strict >, exactly like the reference), so the resulting order — ties included — is the reference's.
+__device__ inline void heapify_packed(uint32_t *heap, int n, int i)
+{
+  uint32_t cur = heap[i];
+  for (;;) {
+    const int left = 2 * i + 1, right = 2 * i + 2;
+    int largest = i;
+    uint32_t big = cur;
+    if (left < n) {
+      const uint32_t l = heap[left];
+      if ((l >> 8) > (big >> 8)) { largest = left; big = l; }
+    }
+    if (right < n) {
+      const uint32_t r = heap[right];
+      if ((r >> 8) > (big >> 8)) { largest = right; big = r; }
+    }
+    if (largest == i) break;
+    heap[i] = big;       // std::swap(pIdx[i], pIdx[largest]) ...
+    heap[largest] = cur; // ... the moved element keeps sinking
+    i = largest;
+  }
+}
+
+// normalize_hist (src/hist.cpp:16-215) by one warp: lanes scale, lane 0 runs the sort and the steal/charity loops.
+// `heap` is 256 u32 of scratch (it may alias the histogram `h`, which is dead once the scaled counts exist).
+__device__ inline void warp_normalize(const uint32_t *h, uint64_t dataBytes, int bits, uint16_t *capped, uint32_t *heap, uint16_t *outCount,
                                       uint32_t lane)
 {
   const uint32_t total = 1u << bits;
   const float mul = __fdiv_rn((float)total, __ull2float_rn(dataBytes));
   uint32_t part = 0;
-  for (int i = lane; i < 256; i += 32) {
-    const float scaled = __fadd_rn(__fmul_rn(__uint2float_rn(h[i]), mul), 0.5f);
+  uint16_t mine[8];
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    const int i = lane + 32 * t;
+    const uint32_t cnt = h[i];
+    const float scaled = __fadd_rn(__fmul_rn(__uint2float_rn(cnt), mul), 0.5f);
     uint16_t c = (uint16_t)__float2uint_rz(scaled);
-    if (c == 0 && h[i]) c = 1;
-    capped[i] = c;
-    idx[i] = (uint8_t)i;
+    if (c == 0 && cnt) c = 1;
+    mine[t] = c;
     part += c;
+  }
+  __syncwarp(); // every lane has read its counts: `heap` may now overwrite `h`
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    const int i = lane + 32 * t;
+    capped[i] = mine[t];
+    heap[i] = ((uint32_t)mine[t] << 8) | (uint32_t)i;
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
   __syncwarp();
   if (lane == 0 && part != total) {
     uint32_t sum = part;
-    for (int i = 256 / 2 - 1; i >= 0; i--) heapify(idx, capped, 256, i);
-    for (int i = 255; i >= 0; i--) {
-      const uint8_t t = idx[0]; idx[0] = idx[i]; idx[i] = t;
-      heapify(idx, capped, i, 0);
+    for (int i = 256 / 2 - 1; i >= 0; i--) heapify_packed(heap, 256, i); // :133-134
+    for (int i = 255; i >= 0; i--) {                                      // :136-140
+      const uint32_t t = heap[0]; heap[0] = heap[i]; heap[i] = t;
+      heapify_packed(heap, i, 0);
     }
+    // heap[] is now the ascending order; the packed values are stale once capped[] changes, so use capped[] below
     int minTwo = 0;
     for (int i = 0; i < 256; i++)
-      if (capped[idx[i]] >= 2) { minTwo = i; break; }
+      if (capped[heap[i] & 0xffu] >= 2) { minTwo = i; break; }
     bool ready = false;
     while (!ready && sum > total) {
       for (int i = minTwo; i < 256; i++) {
-        capped[idx[i]]--; sum--;
+        capped[heap[i] & 0xffu]--; sum--;
         if (sum == total) { ready = true; break; }
       }
       if (ready) break;
       for (int i = minTwo; i < 256; i++)
-        if (capped[idx[i]] >= 2) { minTwo = i; break; }
+        if (capped[heap[i] & 0xffu] >= 2) { minTwo = i; break; }
     }
     while (!ready && sum < total) {
       for (int i = 255; i >= minTwo; i--) {
-        capped[idx[i]]++; sum++;
+        capped[heap[i] & 0xffu]++; sum++;
         if (sum == total) { ready = true; break; }
       }
       if (ready) break;
       for (int i = minTwo; i < 256; i++)
-        if (capped[idx[i]] >= 2) { minTwo = i; break; }
+        if (capped[heap[i] & 0xffu] >= 2) { minTwo = i; break; }
     }
   }
   __syncwarp();
