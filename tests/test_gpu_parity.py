@@ -352,3 +352,25 @@ def test_parallel_device_index_equals_host_walk(gpu, golden):
         except gpu.HsrError:
             got = None
         assert got == host, trial
+
+
+def test_concurrent_host_threads_share_one_device(gpu, golden):
+    """The reference decoders are re-entrant; ours serialise per device behind a mutex."""
+    import threading
+    jobs = [("multi", ck.MT, 64, 15), ("multi", ck.RAW, 64, 12), ("multi", ck.BLOCK, 32, 10), ("runs", ck.MT, 32, 14),
+            ("small", ck.MT, 64, 12), ("multi", ck.MT, 32, 12)]
+    errors = []
+
+    def work(name, fam, states, bits):
+        stream, data = golden[f"stream/{name}/{fam}/{states}/{bits}"], golden[f"in/{name}"]
+        for _ in range(8):
+            n, out = gpu.decode(fam, states, bits, stream, data.size)
+            if n != data.size or not np.array_equal(out[:n], data):
+                errors.append((name, fam, states, bits, n))
+
+    threads = [threading.Thread(target=work, args=j) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
