@@ -8,7 +8,7 @@ argument meaning: (compressed bytes, out_capacity) -> (decoded_length or 0, outp
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Callable, List
+from typing import List
 
 from . import capi
 
