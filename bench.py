@@ -443,6 +443,28 @@ def main():
     comp_total = sum_over_ranks(float(comp))
     units_total = sum_over_ranks(float(units))
 
+    # ---------------------------------------------------------------- optional: assemble the decoded shards on rank 0
+    # NCCL point-to-point over NVLink; not part of the decode roofline, reported apart.
+    assemble = None
+    if world > 1:
+        plans = [pkg.ShardPlan(r, world, 0, 0, r * n, n, 0, 0) for r in range(world)]
+        ps.decode_async(out_dev.data_ptr(), n, cur)
+        torch.cuda.synchronize()
+        pkg.assemble_on(0, out_dev[:n], plans, world * n)   # warm-up (NCCL channel set-up)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        full = pkg.assemble_on(0, out_dev[:n], plans, world * n)
+        a1.record()
+        barrier()
+        if rank == 0:
+            ms = a0.elapsed_time(a1)
+            mine_ok = bool(torch.equal(full[:n], out_dev[:n]))
+            sums = [int(full[r * n:(r + 1) * n][:: 4099].to(torch.int64).sum().item()) for r in range(world)]
+            assemble = {"ms": round(ms, 3), "GBps_into_rank0": round((world - 1) * n / ms / 1e6, 1), "rank0_shard_intact": mine_ok,
+                        "strided_checksums": sums, "transport": "torch.distributed NCCL send/recv"}
+        del full
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -477,6 +499,7 @@ def main():
                     "steps": e2e_steps, "ms_per_step": round(e2e_s / e2e_steps * 1e3, 3), "api": "hsr_decode (host pointers, pinned)"},
             "gpu_launches": int(launches_per_step * a.steps),
             "clocks": clocks, "clocks_e2e": clk2.summary(),
+            "assemble_on_rank0": assemble,
             "index_ms": {"host_walk": round(index_host_ms, 3), "device_walk": round(index_device_ms, 3)},
             "setup_s": {"reference_encode": round(enc_s, 2)},
         }
