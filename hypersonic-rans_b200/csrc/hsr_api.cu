@@ -428,8 +428,12 @@ static bool stream_finish(hsr_stream *s) // uploads the index, allocates the cou
   CU_TRY(cudaMalloc(&s->dCounter, 16), return false);
   CU_TRY(cudaMemset(s->dCounter, 0, 16), return false);
   if (!s->blocks.empty()) {
-    CU_TRY(cudaMalloc(&s->dBlocks, s->blocks.size() * sizeof(hsr_block_t)), return false);
-    CU_TRY(cudaMemcpy(s->dBlocks, s->blocks.data(), s->blocks.size() * sizeof(hsr_block_t), cudaMemcpyHostToDevice), return false);
+    // Units are independent and carry absolute offsets, so the device copy may be in any order: longest first
+    // (LPT), so that the persistent warps' last round consists of the short units and the SMs drain together.
+    std::vector<hsr_block_t> order(s->blocks);
+    std::stable_sort(order.begin(), order.end(), [](const hsr_block_t &a, const hsr_block_t &b) { return a.count > b.count; });
+    CU_TRY(cudaMalloc(&s->dBlocks, order.size() * sizeof(hsr_block_t)), return false);
+    CU_TRY(cudaMemcpy(s->dBlocks, order.data(), order.size() * sizeof(hsr_block_t), cudaMemcpyHostToDevice), return false);
   }
   return true;
 }
@@ -967,6 +971,7 @@ extern "C" size_t hsr_decode_batch(int family, int N, int bits, const uint8_t *i
       return 0;
   } else {
     if (!grow(c->dBlocks, c->blocksCap, units.size())) return 0;
+    std::stable_sort(units.begin(), units.end(), [](const hsr_block_t &a, const hsr_block_t &b) { return a.count > b.count; }); // longest first
     CU_TRY(cudaMemcpyAsync(c->dBlocks, units.data(), units.size() * sizeof(hsr_block_t), cudaMemcpyHostToDevice, c->sRun), return 0);
     if (launch_units(N, bits, c->dIn, inLo, c->dOut, outLo, c->dBlocks, (uint32_t)units.size(), c->dCounters, c->sRun, dStreamStatus) < 0)
       return 0;
