@@ -71,7 +71,9 @@ typedef struct hsr_batch_item {
  * rANS32x64_16w_decode_scalar_<b> (src/rANS32x64_16w.cpp:168) and all their AVX variants,
  * block_rANS32xNN_16w_decode_<b> (src/block_rANS32x32_16w_decode.cpp:165-193),
  * mt_rANS32xNN_16w_decode_<b> / _decode_mt_<b> (src/mt_rANS32x64_16w_decode.cpp:301-361).
- * Uses the current CUDA device (hsr_set_device). Re-entrant across threads; one internal context per device. */
+ * Uses the current CUDA device (hsr_set_device). Re-entrant across threads; one internal context per device.
+ * Limits: decoded length >= stateCount (below that the reference itself is undefined, src/rANS32x32_16w.cpp:206); a
+ * raw stream or a single mt_ block may not exceed 4 GiB of compressed bytes (32-bit word cursor per warp). */
 size_t hsr_decode(int family, int stateCount, int bits, const uint8_t *pInData, size_t inLength, uint8_t *pOutData,
                   size_t outCapacity);
 /* Same, mt_ only, sharding the block chain over `deviceCount` GPUs of this box from ONE process by contiguous
