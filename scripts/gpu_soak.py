@@ -1,0 +1,63 @@
+"""Randomised parity campaign on the GPU (not part of pytest: ~3 min): random codec / length / entropy / stationarity,
+streams from the reference encoders and from the device encoder, every result compared byte for byte.
+    python scripts/gpu_soak.py [--cases 300] [--seed 1]"""
+import argparse, json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import __graft_entry__ as g
+import checkers as ck
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--cases", type=int, default=300)
+ap.add_argument("--seed", type=int, default=1)
+a = ap.parse_args()
+pkg = g.load_package()
+rng = np.random.default_rng(a.seed)
+fails, t0 = [], time.time()
+for case in range(a.cases):
+    fam = int(rng.integers(0, 3))
+    states = int(rng.choice([32, 64]))
+    bits = int(rng.integers(10, 16))
+    kind = rng.random()
+    if kind < 0.5:
+        n = int(rng.integers(states, 5000))
+    elif kind < 0.9:
+        n = int(rng.integers(5000, 600_000))
+    else:
+        n = int(rng.integers(600_000, 6_000_000))
+    s = float(rng.choice([0.0, 0.3, 0.8, 1.0, 1.3, 2.0, 3.5]))
+    seg = int(rng.choice([0, 0, 65536, 4096, 100_000]))
+    data = pkg.synth_zipf(n, s, seed=int(rng.integers(1, 1 << 30)), segment_bytes=seg)
+    if rng.random() < 0.15 and n > 3000:   # splice in single-symbol runs
+        lo = int(rng.integers(0, n // 2)); hi = int(rng.integers(lo, n))
+        data[lo:hi] = int(rng.integers(0, 256))
+    producers = [("ref", lambda: ck.ref_encode(fam, states, bits, data))]
+    if fam == ck.MT:
+        bs = int(rng.choice([0, 0, 32768, 64 * int(rng.integers(1, 3000))]))
+        producers.append((f"dev(bs={bs})", lambda bs=bs: pkg.encode_mt(states, bits, data, bs)))
+    for pname, prod in producers:
+        try:
+            stream = prod()
+        except Exception as exc:
+            if len(set(data.tolist()[:64])) == 1 and np.all(data == data[0]):
+                continue
+            fails.append((case, fam, states, bits, n, pname, f"encode: {exc}")); continue
+        table = int(rng.integers(0, 3))
+        pkg.set_option("table", table)
+        got_n, got = pkg.decode(fam, states, bits, stream, n)
+        pkg.set_option("table", 0)
+        want_n, want = ck.oracle_decode(fam, states, bits, stream, n)
+        if want_n == 0:           # e.g. the reference's constant-input quirk: both must refuse
+            if got_n != 0: fails.append((case, fam, states, bits, n, pname, "oracle refuses, gpu decodes"))
+            continue
+        if got_n != n or not np.array_equal(got[:n], data) or not np.array_equal(want[:n], data):
+            fails.append((case, fam, states, bits, n, pname, f"mismatch got_n={got_n} table={table} err={pkg.last_error()}"))
+        if pname != "ref" and ck.have_ref():
+            rn, ro = ck.ref_decode(fam, states, bits, stream, n, ck.IMPL_POOL if case % 2 else ck.IMPL_SCALAR)
+            if rn != n or not np.array_equal(ro[:n], data):
+                fails.append((case, fam, states, bits, n, pname, "reference decoder rejects the device-encoded stream"))
+print(json.dumps({"cases": a.cases, "failures": len(fails), "seconds": round(time.time() - t0, 1)}))
+for f in fails[:20]:
+    print("FAIL", f)
+sys.exit(1 if fails else 0)
