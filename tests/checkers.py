@@ -149,14 +149,27 @@ def oracle_mt_walk(states: int, stream):
     return [(b.inOffset, b.outOffset, b.size, b.kind) for b in arr[:cnt]]
 
 
+class RefEncoderOverflow(RuntimeError):
+    """The reference encoder wrote outside the capacity its own *_capacity() promises (see ref_encode)."""
+
+
 def ref_encode(family: int, states: int, bits: int, data) -> np.ndarray:
+    """Runs the reference's encoder. Quirk found with the randomised campaign (scripts/gpu_soak.py): on barely
+    compressible input at few probability bits the encoders need more than `*_capacity(n)` bytes — the raw one then
+    memmoves header + words past the end of the caller's buffer (src/rANS32x32_16w.cpp:152-156; its capacity,
+    :10-13, allows only n + 688 bytes) and can even walk below the buffer start. The buffer handed over here is
+    therefore padded on both sides with guard bytes; a touched guard raises RefEncoderOverflow instead of
+    corrupting the heap, and such a stream is not used."""
     d = _u8(data)
     cap = ref().hsref_capacity(family, states, d.size)
-    out = np.zeros(cap + 64, np.uint8)
-    n = ref().hsref_encode(family, states, bits, d.ctypes.data, d.size, out.ctypes.data, cap)
+    front, back = max(4096, d.size // 4), 8192
+    phys = np.full(front + cap + back, 0xAB, np.uint8)
+    n = ref().hsref_encode(family, states, bits, d.ctypes.data, d.size, phys.ctypes.data + front, cap)
+    if not (np.all(phys[:front] == 0xAB) and np.all(phys[front + cap:] == 0xAB)) or n > cap:
+        raise RefEncoderOverflow(f"reference encoder overran its capacity (family {family}, N {states}, bits {bits}, n {d.size})")
     if n == 0:
         raise RuntimeError(f"reference encoder failed (family {family}, N {states}, bits {bits}, n {d.size})")
-    return out[:n].copy()
+    return phys[front: front + n].copy()
 
 
 def ref_decode(family: int, states: int, bits: int, stream, out_capacity: int, impl: int = IMPL_SCALAR):
