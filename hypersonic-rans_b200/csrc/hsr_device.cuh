@@ -28,6 +28,13 @@
 
 #include "../../include/hsrans_b200.h"
 
+// Output path experiment: 1 = stage decoded bytes in a 512-byte shared-memory tile and flush with 16-byte vector
+// stores; 0 = one st.global.u8 per lane and half-row (32 lanes = one full 32-byte sector). Measured on B200
+// (profiles/r1/): see the note at rows_impl.
+#ifndef HSR_OUT_TILE
+#define HSR_OUT_TILE 0
+#endif
+
 namespace hsr {
 
 constexpr uint32_t kConsumePoint16 = 1u << 15; // src/rans.h:8
@@ -97,6 +104,8 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ void st_global_v4(uint8_t *p, uint4 v) { asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
 __device__ __forceinline__ void st_global_u8(uint8_t *p, uint32_t v) { asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------- layout
@@ -127,7 +136,9 @@ struct WarpLayout {
   static constexpr int kOffPacked = kOffSym + kSymBytes;
   static constexpr int kOffRing = kOffPacked + kPackedBytes;
   static constexpr int kOffBar = kOffRing + kRingBytes;   // one mbarrier per ring buffer (TMA bulk copies)
-  static constexpr int kBytes = kOffBar + 32;             // per warp (= per CTA), multiple of 16
+  static constexpr int kOffTile = kOffBar + 32;           // output staging tile (HSR_OUT_TILE experiments)
+  static constexpr int kTileBytes = HSR_OUT_TILE ? 512 : 0;
+  static constexpr int kBytes = kOffTile + kTileBytes;    // per warp (= per CTA), multiple of 16
   static_assert(kBytes % 16 == 0 && kBytes <= 48 * 1024, "static shared memory budget");
 };
 
@@ -423,10 +434,11 @@ template <int BITS, int N, int TK>
 struct Decoder {
   using L = WarpLayout<BITS, N, TK>;
 
-  uint32_t sGrp, sEnt, sSym, sPk; // shared addresses, compile-time constants after inlining
+  uint32_t sGrp, sEnt, sSym, sPk, sTile; // shared addresses, compile-time constants after inlining
 
   __device__ __forceinline__ void init(uint32_t smemWarp)
   {
+    sTile = smemWarp + L::kOffTile;
     sGrp = smemWarp + L::kOffGrp;
     sEnt = smemWarp + L::kOffEnt;
     sSym = smemWarp + L::kOffSym;
@@ -495,7 +507,39 @@ struct Decoder {
   __device__ __forceinline__ void rows_impl(uint32_t &x0, uint32_t &x1, Ring<L> &ring, uint8_t *outLane, uint32_t rows,
                                             uint32_t lane, uint32_t ltMask) const
   {
-    for (uint32_t r = 0; r < rows; r++) {
+    uint32_t r = 0;
+#if HSR_OUT_TILE
+    // tile variant: kTileRows rows are staged in shared memory, then flushed as 32 x 16-byte stores
+    constexpr uint32_t kTileRows = 512 / N;
+    if ((reinterpret_cast<uintptr_t>(outLane - idx2idx_lane(lane)) & 15) == 0) {
+      const uint32_t lanePos = idx2idx_lane(lane);
+      for (; r + kTileRows <= rows; r += kTileRows) {
+#pragma unroll 2
+        for (uint32_t t = 0; t < kTileRows; t++) {
+          ring.advance_if_needed(lane);
+          uint32_t s0, s1 = 0;
+          if constexpr (kMode == 0) {
+            s0 = symbol_step_packed(x0);
+            if constexpr (N == 64) s1 = symbol_step_packed(x1);
+          } else {
+            s0 = symbol_step_rank<kMode == 1>(x0);
+            if constexpr (N == 64) s1 = symbol_step_rank<kMode == 1>(x1);
+          }
+          sts_u8(sTile + t * N + lanePos, s0);
+          renorm(x0, ring.wp, ltMask);
+          if constexpr (N == 64) {
+            sts_u8(sTile + t * N + 32u + lanePos, s1);
+            renorm(x1, ring.wp, ltMask);
+          }
+        }
+        __syncwarp();
+        st_global_v4(outLane - lanePos + lane * 16u, lds_v4(sTile + lane * 16u));
+        __syncwarp();
+        outLane += 512;
+      }
+    }
+#endif
+    for (; r < rows; r++) {
       ring.advance_if_needed(lane);
       uint32_t s0, s1 = 0;
       if constexpr (kMode == 0) {
