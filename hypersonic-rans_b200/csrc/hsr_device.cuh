@@ -13,7 +13,7 @@
 // LDS [reg + imm]. Shared-memory tables (private layouts; only the decoded bytes have to match the reference):
 //   TK_RANK   bitmap-rank table, any bits:
 //               grp[2^b / 16]  u32  {symbol starts before this group : 16 | start bitmap of its 16 slots : 16}
-//               ent[256]       u32  per PRESENT symbol, in slot order {-cumul : 16 | 2^b - freq : 16}
+//               ent[256]       u32  per PRESENT symbol, in slot order {-cumul : 16 | freq - 2^b : 16}, both signed
 //               sym[256]       u8   rank -> symbol (skipped when all 256 symbols are present: rank == symbol)
 //             2^(b-2) + 1.25 KB (9.25 KB at 15 bits vs 33 KB for the reference's hist_dec2_t, src/hist.h:32-37)
 //             and O(256 + 2^b/16) to build instead of O(2^b).
