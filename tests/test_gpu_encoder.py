@@ -121,3 +121,21 @@ def test_full_size_1gb_config4(gpu):
     if ck.have_ref():
         rn, ro = ck.ref_decode(ck.MT, 64, 15, stream, n, ck.IMPL_POOL)
         assert rn == n and np.array_equal(ro[:n], data)
+
+
+def test_encoder_output_is_pinned(gpu):
+    """Multi-block device-encoded streams are deterministic: their SHA-256 is pinned in tests/golden/encoder_hashes.json
+    (generated on a B200 with the same deterministic inputs; single-block streams are pinned against the reference
+    encoder itself above)."""
+    import hashlib, json, os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "encoder_hashes.json")
+    got = {}
+    for states, bits, n, s, seg, bs in ((64, 15, 1_000_031, 1.0, 65536, 0), (32, 12, 700_001, 0.5, 0, 32768),
+                                        (64, 10, 300_000, 2.0, 4096, 65536), (32, 14, 262_144 + 37, 1.3, 65536, 0)):
+        data = gpu.synth_zipf(n, s, seed=1234, segment_bytes=seg)
+        stream = gpu.encode_mt(states, bits, data, bs)
+        got[f"{states}/{bits}/{n}/{s}/{seg}/{bs}"] = hashlib.sha256(stream.tobytes()).hexdigest()
+    if os.environ.get("HSR_WRITE_ENCODER_HASHES") == "1":
+        json.dump(got, open(path, "w"), indent=1, sort_keys=True)
+    want = json.load(open(path))
+    assert got == want
