@@ -35,10 +35,24 @@
 #define HSR_OUT_TILE 0
 #endif
 
+// Build-time knobs of the hot loop (defaults = what measured best on B200, profiles/r1/variants_ring_unroll.jsonl):
+//   HSR_ROW_UNROLL  rows per trip of the hot loop: the loop counter, the branch and the 64-bit output pointer
+//                   amortise over 4 rows (2 -> 4: +1.8 %, 8: no further gain)
+//   HSR_RING2       1: two-buffer word ring with incremental addressing (512 B less shared memory per CTA = 20
+//                   instead of 19 resident CTAs per SM at 15 bits, 24 instead of 31 instructions per refill: +6.3 %)
+//                   0: the three-buffer ring with modulo addressing it replaced
+#ifndef HSR_ROW_UNROLL
+#define HSR_ROW_UNROLL 4
+#endif
+#ifndef HSR_RING2
+#define HSR_RING2 1
+#endif
+
 namespace hsr {
 
 constexpr uint32_t kConsumePoint16 = 1u << 15; // src/rans.h:8
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kRowUnroll = HSR_ROW_UNROLL;
 
 enum TableKind : int { TK_RANK = 1, TK_PACKED = 2 };
 
@@ -125,7 +139,7 @@ struct WarpLayout {
 
   // word ring: kBufs linear segments of kSeg bytes; consecutive segments overlap by one worst-case row
   static constexpr int kSeg = 512;                  // one 16-byte cp.async per lane
-  static constexpr int kBufs = 3;
+  static constexpr int kBufs = HSR_RING2 ? 2 : 3;
   static constexpr int kOverlap = 2 * N;            // a row consumes at most N words
   static constexpr int kStride = kSeg - kOverlap;
   static constexpr int kRingBytes = kSeg * kBufs;
@@ -203,6 +217,72 @@ struct WordRing {
   // bytes consumed from gbase so far
   __device__ __forceinline__ uint32_t cursor() const { return seg * L::kStride + (wp - buf(seg)); }
 
+  __device__ __forceinline__ void drain() const { cp_async_wait<0>(); }
+};
+
+// Two-buffer ring: while the warp reads segment k from one buffer, segment k + 1 is in flight into the other —
+// the buffer the warp left when it crossed into k. The LDS.U16 of the last row read there were issued before the
+// LDGSTS that refills it and have long returned when its data arrives. All addressing is incremental (no modulo):
+// per lane a source offset and a destination that flips between the two buffers.
+template <class L>
+struct WordRing2 {
+  const uint8_t *gbase; // 16-byte aligned
+  uint32_t glimit;      // readable bytes from gbase
+  uint32_t srcOff;      // this lane's source offset of the next segment to issue
+  uint32_t dstNext;     // this lane's shared destination of the next segment to issue
+  uint32_t dstSum;      // dst(buffer 0) + dst(buffer 1)
+  uint32_t cur;         // shared address of the buffer being read
+  uint32_t curSum;      // buffer 0 + buffer 1
+  uint32_t base;        // stream bytes (from gbase) in front of the current buffer
+  uint32_t wp, wlimit;
+
+  __device__ __forceinline__ void issue()
+  {
+    uint32_t bytes = srcOff < glimit ? glimit - srcOff : 0u;
+    bytes = bytes > 16u ? 16u : bytes;
+    cp_async16(dstNext, gbase + (bytes ? srcOff : 0u), bytes); // bytes == 0: zero fill only
+    cp_async_commit();
+    srcOff += (uint32_t)L::kStride;
+    dstNext = dstSum - dstNext;
+  }
+
+  __device__ __forceinline__ void start(uint32_t sbuf, const uint8_t *firstWord, const uint8_t *streamEnd, uint32_t lane)
+  {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(firstWord);
+    gbase = reinterpret_cast<const uint8_t *>(a & ~(uintptr_t)15);
+    const uint64_t avail = (uint64_t)(streamEnd - gbase);
+    glimit = avail > 0xffffffffull ? 0xffffffffu : (uint32_t)avail;
+    srcOff = lane * 16u;
+    dstNext = sbuf + lane * 16u;
+    dstSum = 2u * dstNext + (uint32_t)L::kSeg;
+    cur = sbuf;
+    curSum = 2u * sbuf + (uint32_t)L::kSeg;
+    base = 0;
+    wp = sbuf + (uint32_t)(a & 15);
+    wlimit = sbuf + L::kStride;
+    __syncwarp(); // every lane is done with whatever lived in the ring before
+    issue();
+    issue();
+    cp_async_wait<1>();
+    __syncwarp();
+  }
+
+  __device__ __forceinline__ void advance_if_needed(uint32_t)
+  {
+    if (wp >= wlimit) {
+      const uint32_t into = wp - wlimit; // offset inside the next segment
+      __syncwarp();
+      issue();              // two segments ahead of the one just left, into its buffer
+      cp_async_wait<1>();   // the segment being entered has landed for this lane ...
+      __syncwarp();         // ... and for all the others
+      cur = curSum - cur;
+      base += (uint32_t)L::kStride;
+      wp = cur + into;
+      wlimit = cur + L::kStride;
+    }
+  }
+
+  __device__ __forceinline__ uint32_t cursor() const { return base + (wp - cur); }
   __device__ __forceinline__ void drain() const { cp_async_wait<0>(); }
 };
 
@@ -318,6 +398,8 @@ struct WordRingTma {
 template <class L>
 #if HSR_RING_TMA
 using Ring = WordRingTma<L>;
+#elif HSR_RING2
+using Ring = WordRing2<L>;
 #else
 using Ring = WordRing<L>;
 #endif
@@ -539,6 +621,7 @@ struct Decoder {
       }
     }
 #endif
+#pragma unroll kRowUnroll
     for (; r < rows; r++) {
       ring.advance_if_needed(lane);
       uint32_t s0, s1 = 0;

@@ -10,8 +10,11 @@ namespace hsr {
 #define HSR_NAME(prefix, BITS, TK) HSR_CAT(prefix, HSR_CAT(HSR_N, HSR_CAT(_b, HSR_CAT(BITS, HSR_CAT(_t, TK)))))
 
 // 64 registers keep 32 one-warp CTAs per SM resident (the hardware limit); the decode loop needs ~50.
+#ifndef HSR_UNITS_MIN_CTAS
+#define HSR_UNITS_MIN_CTAS 32
+#endif
 #define HSR_DEFINE(BITS, TK)                                                                                          \
-  __global__ void __launch_bounds__(32, 32) HSR_NAME(units_n, BITS, TK)(DecodeParams p)                               \
+  __global__ void __launch_bounds__(32, HSR_UNITS_MIN_CTAS) HSR_NAME(units_n, BITS, TK)(DecodeParams p)                               \
   { units_kernel_body<BITS, HSR_N, TK>(p); }                                                                          \
   __global__ void __launch_bounds__(32, 16) HSR_NAME(block_n, BITS, TK)(BlockStreamParams p)                           \
   { block_kernel_body<BITS, HSR_N, TK>(p); }

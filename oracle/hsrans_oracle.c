@@ -149,10 +149,20 @@ uint32_t hsro_idx2idx(uint32_t j)
   return (j & ~31u) | (l & 3u) | ((l & 4u) << 2) | ((l & 24u) >> 1);
 }
 
+uint32_t hsro_idx2idx16(uint32_t j)
+{
+  /* src/rANS32x16_16w.cpp:54 (encoder) and :211 (decoder): { 0-3, 8-11, 4-7, 12-15 } */
+  return (j & 3u) | ((j & 4u) << 1) | ((j & 8u) >> 1);
+}
+
+static inline uint32_t lane_pos(uint32_t N, uint32_t j) { return N == 16 ? hsro_idx2idx16(j) : hsro_idx2idx(j); }
+
 size_t hsro_capacity(uint32_t family, uint32_t N, size_t inputSize)
 {
-  if (family == HSRO_RAW)
+  if (family == HSRO_RAW) /* also src/rANS32x16_16w.cpp:10-13 */
     return inputSize + N + sizeof(uint16_t) * 256 + sizeof(uint32_t) * N + sizeof(uint64_t) * 2;
+  if (family == HSRO_RAW32BLK) /* src/rans32x32_32blk_16w.cpp:10-13 */
+    return inputSize + N + sizeof(uint16_t) * 256 + sizeof(uint32_t) * N * 2 + sizeof(uint64_t) * 2;
   const size_t minMinBlockSize = (size_t)1 << 15; /* src/block_rANS32x32_16w_encode.cpp:12-13 */
   const size_t baseSize = 2 * sizeof(uint64_t) + 256 * sizeof(uint16_t) + inputSize + N * sizeof(uint32_t);
   const size_t blockCount = (inputSize + minMinBlockSize) / minMinBlockSize + 1;
@@ -196,7 +206,7 @@ static size_t rows(dec_state_t *d, uint8_t *out, size_t i, size_t end)
 {
   for (; i < end; i += d->N) {
     for (uint32_t j = 0; j < d->N; j++)
-      out[i + hsro_idx2idx(j)] = step(d, j);
+      out[i + lane_pos(d->N, j)] = step(d, j);
     if (d->overrun)
       return i;
   }
@@ -207,7 +217,7 @@ static size_t rows(dec_state_t *d, uint8_t *out, size_t i, size_t end)
 static void tail(dec_state_t *d, uint8_t *out, size_t i, size_t n)
 {
   for (uint32_t j = 0; j < d->N; j++) {
-    const uint32_t index = hsro_idx2idx(j);
+    const uint32_t index = lane_pos(d->N, j);
     if (i + index < n)
       out[i + index] = step(d, j);
   }
@@ -220,9 +230,9 @@ typedef struct header {
 static int read_header(uint32_t N, uint32_t bits, const uint8_t *in, size_t inLength, size_t outCapacity,
                        header_t *h)
 {
-  if (!(N == 32 || N == 64) || bits < 10 || bits > 15)
+  if (!(N == 16 || N == 32 || N == 64) || bits < 10 || bits > 15)
     return 0;
-  if (inLength < 16 + 4 * (size_t)N + 512) /* src/rANS32x32_16w.cpp:164 */
+  if (inLength < 16 + 4 * (size_t)N + 512) /* src/rANS32x32_16w.cpp:164, src/rANS32x16_16w.cpp:165 */
     return 0;
   h->n = rd64(in);
   if (h->n > outCapacity) /* :173 */
@@ -265,6 +275,81 @@ size_t hsro_decode_raw(uint32_t N, uint32_t bits, const uint8_t *in, size_t inLe
   if (d->overrun)
     return 0;
   return h.n;
+}
+
+/* ------------------------------------------------------------------ rANS32x32_32blk_16w */
+
+/* src/rans32x32_32blk_16w.cpp:183-301. Same header as raw, then u32 blockSize[31] (bytes of the word sub-stream of
+ * states 0..30; the last one needs none, :160-167) and the 32 sub-streams back to back: state j reads its words
+ * from its OWN head pReadHead[j] (:224-233), so there is no shared cursor. */
+static int step_32blk(dec_state_t *d, const uint8_t **rd, const uint8_t *end, uint32_t j, uint8_t *sym)
+{
+  const uint32_t mask = (1u << d->bits) - 1;
+  uint32_t x = d->states[j];
+  const uint32_t slot = x & mask;
+  const uint8_t s = d->cumulInv[slot]; /* :17-30 */
+  *sym = s;
+  x = (x >> d->bits) * (uint32_t)d->hist.symbolCount[s] + slot - (uint32_t)d->hist.cumul[s];
+  if (x < CONSUME_POINT16) { /* :258-262: this state's own read head */
+    if (rd[j] + 2 > end)
+      return 0;
+    x = (x << 16) | rd16(rd[j]);
+    rd[j] += 2;
+  }
+  d->states[j] = x;
+  return 1;
+}
+
+size_t hsro_decode_32blk(uint32_t bits, const uint8_t *in, size_t inLength, uint8_t *out, size_t outCapacity)
+{
+  const uint32_t N = 32;
+  if (bits < 10 || bits > 15)
+    return 0;
+  if (inLength < 16 + 4 * (size_t)(2 * N - 1) + 512) /* :185 */
+    return 0;
+  const uint64_t n = rd64(in);
+  if (n > outCapacity) /* :194 */
+    return 0;
+  const uint64_t compLen = rd64(in + 8);
+  if (inLength < compLen) /* :200 */
+    return 0;
+  if (n < N) /* size_t wrap at :238, undefined in the reference; refuse */
+    return 0;
+
+  static dec_state_t sd;
+  dec_state_t *d = &sd;
+  memset(d, 0, sizeof(*d));
+  d->N = N; d->bits = bits;
+  for (size_t i = 0; i < 256; i++) /* :205-209 */
+    d->hist.symbolCount[i] = rd16(in + 16 + 2 * i);
+  if (!hsro_make_cumul_inv(&d->hist, bits, d->cumulInv)) /* :211 */
+    return 0;
+  for (uint32_t j = 0; j < N; j++) /* :216-220 */
+    d->states[j] = rd32(in + 16 + 512 + 4 * j);
+
+  const uint8_t *sizes = in + 16 + 512 + 4 * (size_t)N;
+  const uint8_t *end = in + inLength;
+  const uint8_t *rd[32];
+  rd[0] = sizes + 4 * (size_t)(N - 1); /* :223 */
+  for (uint32_t j = 1; j < N; j++) {   /* :225-231 */
+    const uint32_t blockSize = rd32(sizes + 4 * (size_t)(j - 1));
+    if ((size_t)(end - rd[j - 1]) < blockSize)
+      return 0; /* the reference would read out of bounds here */
+    rd[j] = rd[j - 1] + blockSize;
+  }
+
+  const size_t outLengthInStates = n - N + 1; /* :238 */
+  size_t i = 0;
+  for (; i < outLengthInStates; i += N) /* full rows, :241-269 */
+    for (uint32_t j = 0; j < N; j++)
+      if (!step_32blk(d, rd, end, j, &out[i + hsro_idx2idx(j)]))
+        return 0;
+  for (uint32_t j = 0; j < N; j++) { /* the < 32 leftover symbols, :271-298 */
+    const uint32_t index = hsro_idx2idx(j);
+    if (i + index < n && !step_32blk(d, rd, end, j, &out[i + index]))
+      return 0;
+  }
+  return n;
 }
 
 /* ------------------------------------------------------------------ block_ and mt_ */
@@ -367,12 +452,16 @@ static size_t decode_blocked(int mt, uint32_t N, uint32_t bits, const uint8_t *i
 size_t hsro_decode_block(uint32_t N, uint32_t bits, const uint8_t *in, size_t inLength, uint8_t *out,
                          size_t outCapacity)
 {
+  if (N == 16)
+    return 0; /* no 16-state block_ codec exists */
   return decode_blocked(0, N, bits, in, inLength, out, outCapacity);
 }
 
 size_t hsro_decode_mt(uint32_t N, uint32_t bits, const uint8_t *in, size_t inLength, uint8_t *out,
                       size_t outCapacity)
 {
+  if (N == 16)
+    return 0;
   return decode_blocked(1, N, bits, in, inLength, out, outCapacity);
 }
 
@@ -383,6 +472,7 @@ size_t hsro_decode(uint32_t family, uint32_t N, uint32_t bits, const uint8_t *in
   case HSRO_RAW: return hsro_decode_raw(N, bits, in, inLength, out, outCapacity);
   case HSRO_BLOCK: return hsro_decode_block(N, bits, in, inLength, out, outCapacity);
   case HSRO_MT: return hsro_decode_mt(N, bits, in, inLength, out, outCapacity);
+  case HSRO_RAW32BLK: return N == 32 ? hsro_decode_32blk(bits, in, inLength, out, outCapacity) : 0;
   default: return 0;
   }
 }
@@ -441,9 +531,9 @@ size_t hsro_mt_walk(uint32_t N, const uint8_t *in, size_t inLength, hsro_mt_bloc
 size_t hsro_encode_raw(uint32_t N, uint32_t bits, const uint8_t *in, size_t length, uint8_t *out,
                        size_t outCapacity, const hsro_hist_t *hist)
 {
-  if (!(N == 32 || N == 64) || bits < 10 || bits > 15 || length == 0)
+  if (!(N == 16 || N == 32 || N == 64) || bits < 10 || bits > 15 || length == 0)
     return 0;
-  if (outCapacity < hsro_capacity(HSRO_RAW, N, length)) /* src/rANS32x32_16w.cpp:37 */
+  if (outCapacity < hsro_capacity(HSRO_RAW, N, length)) /* src/rANS32x32_16w.cpp:37, src/rANS32x16_16w.cpp:37 */
     return 0;
   const uint32_t emitPoint = (CONSUME_POINT16 >> bits) << 16; /* :41 */
   uint32_t states[64];
@@ -460,7 +550,7 @@ size_t hsro_encode_raw(uint32_t N, uint32_t bits, const uint8_t *in, size_t leng
 
   for (; i >= (int64_t)N; i -= N) { /* first pass is the ragged row (:59-95), then full rows (:99-128) */
     for (int64_t j = (int64_t)N - 1; j >= 0; j--) {
-      const int64_t pos = i - (int64_t)N + (int64_t)hsro_idx2idx((uint32_t)j);
+      const int64_t pos = i - (int64_t)N + (int64_t)lane_pos(N, (uint32_t)j);
       if (pos >= (int64_t)length)
         continue;
       const uint8_t sym = in[pos];
