@@ -7,8 +7,9 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-HSR_RAW, HSR_BLOCK, HSR_MT = 0, 1, 2
-FAMILY_NAMES = {HSR_RAW: "rANS32x{N}_16w", HSR_BLOCK: "block_rANS32x{N}_16w", HSR_MT: "mt_rANS32x{N}_16w"}
+HSR_RAW, HSR_BLOCK, HSR_MT, HSR_RAW32BLK = 0, 1, 2, 3
+FAMILY_NAMES = {HSR_RAW: "rANS32x{N}_16w", HSR_BLOCK: "block_rANS32x{N}_16w", HSR_MT: "mt_rANS32x{N}_16w",
+                HSR_RAW32BLK: "rANS32x{N}_32blk_16w"}
 HSR_OUT_SHARD_LOCAL = 1
 
 

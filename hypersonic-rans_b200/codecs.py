@@ -2,7 +2,7 @@
 
 The reference registers one row per (codec family, probability bits) holding function pointers of type
 `decodeFunc` (main.cpp:149). Here each row carries the name the reference prints for that codec
-(main.cpp:174-214), the C-ABI triple (family, state count, bits) and a `decode` callable with the reference's
+(main.cpp:174-228), the C-ABI triple (family, state count, bits) and a `decode` callable with the reference's
 argument meaning: (compressed bytes, out_capacity) -> (decoded_length or 0, output buffer).
 """
 from __future__ import annotations
@@ -38,6 +38,11 @@ def _rows() -> List[Codec]:
                               capi.HSR_BLOCK, n_states, bits))
             rows.append(Codec(f"rANS32x{n_states} 16w {bits} mt", f"mt_rANS32x{n_states}_16w_decode_{bits}",
                               capi.HSR_MT, n_states, bits))
+    for bits in (15, 14, 13, 12, 11, 10):  # main.cpp:216-228
+        rows.append(Codec(f"rANS32x16 16w {bits} (raw)", f"rANS32x16_16w_decode_scalar_{bits}", capi.HSR_RAW, 16, bits))
+    for bits in (15, 14, 13, 12, 11, 10):
+        rows.append(Codec(f"rANS32x32 32blk 16w {bits} (raw)", f"rANS32x32_32blk_16w_decode_scalar_{bits}",
+                          capi.HSR_RAW32BLK, 32, bits))
     return rows
 
 

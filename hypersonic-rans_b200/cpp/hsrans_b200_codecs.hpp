@@ -11,6 +11,8 @@
 //     cuda_block_rANS32x64_16w_decode_<b>    replaces block_rANS32x64_16w_decode_<b>    (src/block_rANS32x64_16w.h:15-20)
 //     cuda_mt_rANS32x32_16w_decode_<b>       replaces mt_rANS32x32_16w_decode_<b> and _decode_mt_<b> (src/mt_rANS32x32_16w.h:16-28)
 //     cuda_mt_rANS32x64_16w_decode_<b>       replaces mt_rANS32x64_16w_decode_<b> and _decode_mt_<b> (src/mt_rANS32x64_16w.h:16-28)
+//     cuda_rANS32x16_16w_decode_<b>          replaces rANS32x16_16w_decode_scalar_<b>   (src/rANS32x16_16w.h:9 ...)
+//     cuda_rANS32x32_32blk_16w_decode_<b>    replaces rANS32x32_32blk_16w_decode_scalar_<b> (src/rans32x32_32blk_16w.h:9 ...)
 // for <b> in 10..15, plus the `*_capacity` twins. Same return convention: decoded size, or 0 on any error.
 // The mt_ thread-pool variants take no pool here: the GPU is the pool (hsr_decode_mt_multi spreads one stream
 // over several GPUs the way decode_mt spreads it over threads, src/mt_rANS32x64_16w_decode.cpp:137-265).
@@ -42,6 +44,8 @@ HSR_B200_DECODERS(cuda_block_rANS32x32_16w_decode, HSR_BLOCK, 32)
 HSR_B200_DECODERS(cuda_block_rANS32x64_16w_decode, HSR_BLOCK, 64)
 HSR_B200_DECODERS(cuda_mt_rANS32x32_16w_decode, HSR_MT, 32)
 HSR_B200_DECODERS(cuda_mt_rANS32x64_16w_decode, HSR_MT, 64)
+HSR_B200_DECODERS(cuda_rANS32x16_16w_decode, HSR_RAW, 16)
+HSR_B200_DECODERS(cuda_rANS32x32_32blk_16w_decode, HSR_RAW32BLK, 32)
 
 #undef HSR_B200_DECODERS
 #undef HSR_B200_DECODER
@@ -53,6 +57,9 @@ inline size_t cuda_block_rANS32x32_16w_capacity(const size_t inputSize) { return
 inline size_t cuda_block_rANS32x64_16w_capacity(const size_t inputSize) { return hsr_capacity(HSR_BLOCK, 64, inputSize); }
 inline size_t cuda_mt_rANS32x32_16w_capacity(const size_t inputSize) { return hsr_capacity(HSR_MT, 32, inputSize); }
 inline size_t cuda_mt_rANS32x64_16w_capacity(const size_t inputSize) { return hsr_capacity(HSR_MT, 64, inputSize); }
+// src/rANS32x16_16w.cpp:10-13, src/rans32x32_32blk_16w.cpp:10-13
+inline size_t cuda_rANS32x16_16w_capacity(const size_t inputSize) { return hsr_capacity(HSR_RAW, 16, inputSize); }
+inline size_t cuda_rANS32x32_32blk_16w_capacity(const size_t inputSize) { return hsr_capacity(HSR_RAW32BLK, 32, inputSize); }
 
 // Device producers with the reference's mt_ encoder signature (src/mt_rANS32x64_16w.h:9-14):
 //     size_t mt_rANS32x64_16w_encode_<b>(const uint8_t *pInData, const size_t length, uint8_t *pOutData, const size_t outCapacity)

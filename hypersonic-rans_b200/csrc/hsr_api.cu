@@ -2,7 +2,8 @@
 // sharding, device contexts, the host<->device pipeline and the kernel launches.
 //
 // Mirrors the framing logic of the reference's decode entry points (error returns included):
-//   raw    src/rANS32x32_16w.cpp:161-201          block_  src/block_rANS32x32_16w_decode.cpp:18-96
+//   raw    src/rANS32x32_16w.cpp:161-201 (16 states: src/rANS32x16_16w.cpp:162-203; 32blk: src/rans32x32_32blk_16w.cpp:183-231)
+//   block_ src/block_rANS32x32_16w_decode.cpp:18-96
 //   mt_    src/mt_rANS32x64_16w_decode.cpp:12-97  (the serial header walk of :40-66,94 becomes hsr_mt_index)
 // There is no CPU decode path in this file: without a CUDA device every compute entry point fails.
 #include <algorithm>
@@ -97,6 +98,8 @@ extern "C" size_t hsr_capacity(int family, int N, size_t inputSize)
   const size_t n = (size_t)N;
   if (family == HSR_RAW) // src/rANS32x32_16w.cpp:10-13: buffer + one row of slack + histogram + states + lengths
     return inputSize + n + sizeof(uint16_t) * 256 + sizeof(uint32_t) * n + sizeof(uint64_t) * 2;
+  if (family == HSR_RAW32BLK) // src/rans32x32_32blk_16w.cpp:10-13: + the sub-stream sizes
+    return inputSize + n + sizeof(uint16_t) * 256 + sizeof(uint32_t) * n * 2 + sizeof(uint64_t) * 2;
   // src/block_rANS32x32_16w_encode.cpp:47-54 / src/mt_rANS32x64_16w_encode.cpp:50-57: one header per possible
   // block of MinMinBlockSize = 2^15 symbols; mt_ headers also carry the skip offset and a state snapshot
   const size_t base = 2 * sizeof(uint64_t) + 256 * sizeof(uint16_t) + inputSize + n * sizeof(uint32_t);
@@ -128,13 +131,25 @@ struct Header {
 
 static bool valid_codec(int family, int N, int bits)
 {
-  return family >= HSR_RAW && family <= HSR_MT && (N == 32 || N == 64) && bits >= 10 && bits <= 15;
+  if (bits < 10 || bits > 15) return false;
+  if (family == HSR_RAW) return N == 16 || N == 32 || N == 64; // rANS32x16_16w, rANS32x32_16w, rANS32x64_16w
+  if (family == HSR_RAW32BLK) return N == 32;                   // rANS32x32_32blk_16w
+  return (family == HSR_BLOCK || family == HSR_MT) && (N == 32 || N == 64);
+}
+
+static inline bool is_raw_family(int family) { return family == HSR_RAW || family == HSR_RAW32BLK; }
+
+// bytes in front of the first word: lengths, counts, states (+ the 31 sub-stream sizes of the 32blk layout,
+// src/rans32x32_32blk_16w.cpp:185)
+static inline uint64_t fixed_header_bytes(int family, int N)
+{
+  return 16 + 512 + 4 * (uint64_t)(family == HSR_RAW32BLK ? 2 * N - 1 : N);
 }
 
 // the checks every reference decoder starts with (src/rANS32x32_16w.cpp:164-180)
-static bool read_header(int N, const uint8_t *in, size_t inLength, size_t outCapacity, Header *h)
+static bool read_header(int family, int N, const uint8_t *in, size_t inLength, size_t outCapacity, Header *h)
 {
-  if (!in || inLength < 16 + 4 * (size_t)N + 512) { set_err("input shorter than the fixed header"); return false; }
+  if (!in || inLength < fixed_header_bytes(family, N)) { set_err("input shorter than the fixed header"); return false; }
   h->n = rd64(in);
   h->compLen = rd64(in + 8);
   if (h->n > outCapacity) { set_err("decoded length %llu exceeds outCapacity %zu", (unsigned long long)h->n, outCapacity); return false; }
@@ -243,7 +258,12 @@ static int pick_table(int bits, size_t units = (size_t)-1)
   return bits <= 11 ? TK_PACKED : TK_RANK;
 }
 
-static const KernelEntry &kernel_entry(int N, int bits, int table) { return (N == 32 ? kKernels32 : kKernels64)[bits - 10][table - 1]; }
+static const KernelEntry &kernel_entry(int family, int N, int bits, int table)
+{
+  if (family == HSR_RAW32BLK) return kKernelsBlk32[bits - 10];
+  if (N == 16) return kKernelsRaw16[bits - 10];
+  return (N == 32 ? kKernels32 : kKernels64)[bits - 10][table - 1];
+}
 
 struct LaunchInfo {
   int ctasPerSm = 0, smCount = 0;
@@ -272,13 +292,13 @@ static bool prepare_kernel(const void *fn, LaunchInfo *li)
 }
 
 // launches the units kernel over `numBlocks` records of a device-resident index
-static int launch_units(int N, int bits, const uint8_t *dIn, uint64_t inBase, uint8_t *dOut, uint64_t outBase,
+static int launch_units(int family, int N, int bits, const uint8_t *dIn, uint64_t inBase, uint8_t *dOut, uint64_t outBase,
                         const hsr_block_t *dBlocks, uint32_t numBlocks, uint32_t *dCounter, cudaStream_t st,
                         uint32_t *dStreamStatus = nullptr)
 {
   if (numBlocks == 0) return 0;
   const int table = pick_table(bits, numBlocks);
-  const KernelEntry &ke = kernel_entry(N, bits, table);
+  const KernelEntry &ke = kernel_entry(family, N, bits, table);
   DecodeParams p{dIn, inBase, dOut, outBase, dBlocks, numBlocks, dCounter, dStreamStatus};
   void *args[] = {&p};
   CU_TRY(cudaMemsetAsync(dCounter, 0, 4, st), return -1); // work counter only; status bits accumulate
@@ -296,7 +316,7 @@ static int launch_block_stream(int N, int bits, const uint8_t *dIn, uint64_t inL
                                uint32_t *dCounter, cudaStream_t st)
 {
   const int table = pick_table(bits, 1);
-  const KernelEntry &ke = kernel_entry(N, bits, table);
+  const KernelEntry &ke = kernel_entry(HSR_BLOCK, N, bits, table);
   BlockStreamParams p{dIn, dOut, nullptr, BlockStreamDesc{0, inLength, 0, n}, 1u, dCounter, nullptr};
   void *args[] = {&p};
   CU_TRY(cudaLaunchKernel(ke.block, dim3(1), dim3(32), args, 0, st), return -1);
@@ -309,7 +329,7 @@ static int launch_block_batch(int N, int bits, const uint8_t *dIn, uint8_t *dOut
 {
   if (count == 0) return 0;
   const int table = pick_table(bits, count);
-  const KernelEntry &ke = kernel_entry(N, bits, table);
+  const KernelEntry &ke = kernel_entry(HSR_BLOCK, N, bits, table);
   BlockStreamParams p{dIn, dOut, dStreams, BlockStreamDesc{0, 0, 0, 0}, count, dCounter, dStreamStatus};
   void *args[] = {&p};
   CU_TRY(cudaMemsetAsync(dCounter, 0, 4, st), return -1);
@@ -438,14 +458,14 @@ static bool stream_finish(hsr_stream *s) // uploads the index, allocates the cou
   return true;
 }
 
-static hsr_block_t raw_unit(int N, const Header &h)
+static hsr_block_t raw_unit(int family, int N, const Header &h)
 {
   hsr_block_t b{};
   b.inOffset = 16; // u16 counts[256], then u32 states[N], then words (src/rANS32x32_16w.cpp:183-200)
   b.inEnd = h.compLen;
   b.outOffset = 0;
   b.count = h.n;
-  b.kind = 2;
+  b.kind = family == HSR_RAW32BLK ? 3 : 2; // 3: + u32 blockSize[31], then 32 private sub-streams
   b.tail = (uint32_t)(h.n % (uint64_t)N);
   return b;
 }
@@ -468,8 +488,8 @@ static bool plan_batch(int family, int N, const uint8_t *inBase, const hsr_batch
   // per-stream header checks (src/rANS32x32_16w.cpp:164-180); bad streams get length 0 and are skipped
   for (size_t i = 0; i < count; i++) {
     const hsr_batch_item_t &it = items[i];
-    if (!read_header(N, inBase + it.inOffset, (size_t)it.inLength, (size_t)it.outCapacity, &bp->hdr[i])) continue;
-    if (bp->hdr[i].compLen < 16 + 4 * (uint64_t)N + 512 || bp->hdr[i].compLen > kMaxUnitIn) continue;
+    if (!read_header(family, N, inBase + it.inOffset, (size_t)it.inLength, (size_t)it.outCapacity, &bp->hdr[i])) continue;
+    if (bp->hdr[i].compLen < fixed_header_bytes(family, N) || bp->hdr[i].compLen > kMaxUnitIn) continue;
     bp->good[i] = 1;
     nGood++;
     bp->inLo = std::min<uint64_t>(bp->inLo, it.inOffset & ~15ull);
@@ -481,8 +501,8 @@ static bool plan_batch(int family, int N, const uint8_t *inBase, const hsr_batch
   for (size_t i = 0; i < count; i++) {
     if (!bp->good[i]) continue;
     const hsr_batch_item_t &it = items[i];
-    if (family == HSR_RAW) {
-      hsr_block_t u = raw_unit(N, bp->hdr[i]);
+    if (is_raw_family(family)) {
+      hsr_block_t u = raw_unit(family, N, bp->hdr[i]);
       u.inOffset += it.inOffset; u.inEnd += it.inOffset; u.outOffset += it.outOffset; u.reserved = (uint32_t)i;
       bp->units.push_back(u);
     } else if (family == HSR_MT) {
@@ -510,8 +530,8 @@ extern "C" hsr_stream_t *hsr_stream_upload(int family, int N, int bits, const ui
   if (shards < 1 || shard < 0 || shard >= shards) { set_err("bad shard %d of %d", shard, shards); return nullptr; }
   if (family != HSR_MT && shards != 1) { set_err("only mt_ streams shard; raw and block_ are one recurrence"); return nullptr; }
   Header h;
-  if (!read_header(N, in, inLength, (size_t)-1, &h)) return nullptr;
-  if (h.compLen < 16 + 4 * (uint64_t)N + 512) { set_err("compressed length field too small"); return nullptr; }
+  if (!read_header(family, N, in, inLength, (size_t)-1, &h)) return nullptr;
+  if (h.compLen < fixed_header_bytes(family, N)) { set_err("compressed length field too small"); return nullptr; }
 
   std::unique_ptr<hsr_stream, void (*)(hsr_stream *)> s(new hsr_stream, stream_release);
   s->family = family; s->N = N; s->bits = bits; s->n = h.n; s->compLen = h.compLen;
@@ -537,9 +557,9 @@ extern "C" hsr_stream_t *hsr_stream_upload(int family, int N, int bits, const ui
       lo = hi = 0;
     }
   } else {
-    if (family == HSR_RAW) {
+    if (is_raw_family(family)) {
       if (h.compLen > kMaxUnitIn) { set_err("raw streams above 4 GiB compressed are not supported"); return nullptr; }
-      s->blocks.push_back(raw_unit(N, h));
+      s->blocks.push_back(raw_unit(family, N, h));
     }
     s->outOffset = 0;
     s->outBytes = h.n;
@@ -561,12 +581,12 @@ extern "C" hsr_stream_t *hsr_stream_from_device(int family, int N, int bits, con
   if (!valid_codec(family, N, bits)) { set_err("unsupported codec (family %d, N %d, bits %d)", family, N, bits); return nullptr; }
   const uint8_t *dIn = static_cast<const uint8_t *>(dInV);
   if (!dIn || (reinterpret_cast<uintptr_t>(dIn) & 15)) { set_err("device input must be 16-byte aligned"); return nullptr; }
-  if (inLength < 16 + 4 * (size_t)N + 512) { set_err("input shorter than the fixed header"); return nullptr; }
+  if (inLength < fixed_header_bytes(family, N)) { set_err("input shorter than the fixed header"); return nullptr; }
   uint8_t hdr[16];
   CU_TRY(cudaMemcpy(hdr, dIn, 16, cudaMemcpyDeviceToHost), return nullptr);
   Header h{rd64(hdr), rd64(hdr + 8)};
   if (inLength < h.compLen) { set_err("inLength %zu < compressed length %llu", inLength, (unsigned long long)h.compLen); return nullptr; }
-  if (h.n < (uint64_t)N || h.compLen < 16 + 4 * (uint64_t)N + 512) { set_err("malformed header"); return nullptr; }
+  if (h.n < (uint64_t)N || h.compLen < fixed_header_bytes(family, N)) { set_err("malformed header"); return nullptr; }
 
   std::unique_ptr<hsr_stream, void (*)(hsr_stream *)> s(new hsr_stream, stream_release);
   s->family = family; s->N = N; s->bits = bits; s->n = h.n; s->compLen = h.compLen;
@@ -578,9 +598,9 @@ extern "C" hsr_stream_t *hsr_stream_from_device(int family, int N, int bits, con
   s->outOffset = 0;
   s->outBytes = h.n;
 
-  if (family == HSR_RAW) {
+  if (is_raw_family(family)) {
     if (h.compLen > kMaxUnitIn) { set_err("raw streams above 4 GiB compressed are not supported"); return nullptr; }
-    s->blocks.push_back(raw_unit(N, h));
+    s->blocks.push_back(raw_unit(family, N, h));
   } else if (family == HSR_MT) {
     // segment-parallel index first (hsr_index.cu); the serial walk below is the fallback and the error reporter
     const long indexMode = g_optIndex;
@@ -686,7 +706,7 @@ extern "C" int hsr_stream_decode_async(hsr_stream_t *s, void *dOutV, size_t outC
     return launch_block_batch(s->N, s->bits, s->dIn, dOut, s->dDescs, s->numDescs, s->dCounter, nullptr, st);
   if (s->family == HSR_BLOCK)
     return launch_block_stream(s->N, s->bits, s->dIn, s->compLen, dOut, s->n, s->dCounter, st);
-  return launch_units(s->N, s->bits, s->dIn, s->inBase, dOut, outBase, s->dBlocks, (uint32_t)s->blocks.size(), s->dCounter, st);
+  return launch_units(s->family, s->N, s->bits, s->dIn, s->inBase, dOut, outBase, s->dBlocks, (uint32_t)s->blocks.size(), s->dCounter, st);
 }
 
 extern "C" unsigned hsr_stream_status(hsr_stream_t *s)
@@ -799,8 +819,8 @@ static bool start_h2d(DeviceCtx *c, const uint8_t *in, uint64_t lo, uint64_t hi,
 // Decodes units [first, last) whose compressed bytes are arriving through `fl`: contiguous unit ranges are
 // launched as soon as the copy piece holding their last byte has landed, and each range's decoded bytes go back
 // to the host while later ranges are still decoding (three streams: copy-in, run, copy-out).
-static bool run_units_pipelined(DeviceCtx *c, int N, int bits, uint8_t *out, const hsr_block_t *units, size_t first, size_t last,
-                                const InFlight &fl)
+static bool run_units_pipelined(DeviceCtx *c, int family, int N, int bits, uint8_t *out, const hsr_block_t *units, size_t first,
+                                size_t last, const InFlight &fl)
 {
   if (first >= last) return true;
   const uint64_t outLo = units[first].outOffset, outHi = units[last - 1].outOffset + units[last - 1].count;
@@ -840,7 +860,7 @@ static bool run_units_pipelined(DeviceCtx *c, int N, int bits, uint8_t *out, con
     const uint64_t needEnd = units[b - 1].inEnd;
     while (piece + 1 < fl.ends.size() && fl.ends[piece] < needEnd) piece++;
     CU_TRY(cudaStreamWaitEvent(c->sRun, c->evIn[piece], 0), return false);
-    if (launch_units(N, bits, c->dIn, fl.lo, c->dOut, outLo, devBlocks + (a - first), (uint32_t)(b - a), c->dCounters + 4 * r, c->sRun) < 0)
+    if (launch_units(family, N, bits, c->dIn, fl.lo, c->dOut, outLo, devBlocks + (a - first), (uint32_t)(b - a), c->dCounters + 4 * r, c->sRun) < 0)
       return false;
     CU_TRY(cudaEventRecord(c->evRun[r], c->sRun), return false);
     CU_TRY(cudaStreamWaitEvent(c->sOut, c->evRun[r], 0), return false);
@@ -859,7 +879,7 @@ static bool run_units_pipelined(DeviceCtx *c, int N, int bits, uint8_t *out, con
 }
 
 // units [first, last) of an already indexed stream, from host memory, on `device`
-static bool decode_units_from_host(int device, int N, int bits, const uint8_t *in, uint8_t *out, const hsr_block_t *units,
+static bool decode_units_from_host(int device, int family, int N, int bits, const uint8_t *in, uint8_t *out, const hsr_block_t *units,
                                    size_t first, size_t last)
 {
   if (first >= last) return true;
@@ -869,7 +889,7 @@ static bool decode_units_from_host(int device, int N, int bits, const uint8_t *i
   std::lock_guard<std::mutex> lock(c->mu);
   InFlight fl;
   if (!start_h2d(c, in, units[first].inOffset & ~15ull, units[last - 1].inEnd, &fl)) return false;
-  return run_units_pipelined(c, N, bits, out, units, first, last, fl);
+  return run_units_pipelined(c, family, N, bits, out, units, first, last, fl);
 }
 
 static bool decode_block_from_host(int device, int N, int bits, const uint8_t *in, const Header &h, uint8_t *out)
@@ -897,18 +917,18 @@ extern "C" size_t hsr_decode(int family, int N, int bits, const uint8_t *in, siz
   g_err.clear();
   if (!valid_codec(family, N, bits)) { set_err("unsupported codec (family %d, N %d, bits %d)", family, N, bits); return 0; }
   Header h;
-  if (!read_header(N, in, inLength, outCapacity, &h)) return 0;
+  if (!read_header(family, N, in, inLength, outCapacity, &h)) return 0;
   if (!out) { set_err("null output"); return 0; }
-  if (h.compLen < 16 + 4 * (uint64_t)N + 512) { set_err("compressed length field too small"); return 0; }
+  if (h.compLen < fixed_header_bytes(family, N)) { set_err("compressed length field too small"); return 0; }
   int device = 0;
   CU_TRY(cudaGetDevice(&device), return 0);
 
   if (family == HSR_BLOCK)
     return decode_block_from_host(device, N, bits, in, h, out) ? (size_t)h.n : 0;
-  if (family == HSR_RAW) {
+  if (is_raw_family(family)) {
     if (h.compLen > kMaxUnitIn) { set_err("raw streams above 4 GiB compressed are not supported"); return 0; }
-    const hsr_block_t u = raw_unit(N, h);
-    return decode_units_from_host(device, N, bits, in, out, &u, 0, 1) ? (size_t)h.n : 0;
+    const hsr_block_t u = raw_unit(family, N, h);
+    return decode_units_from_host(device, family, N, bits, in, out, &u, 0, 1) ? (size_t)h.n : 0;
   }
   // mt_: start moving the whole stream to the device, walk the header chain on the host meanwhile
   DeviceCtx *c = get_ctx(device);
@@ -926,7 +946,7 @@ extern "C" size_t hsr_decode(int family, int N, int bits, const uint8_t *in, siz
     cudaStreamSynchronize(c->sIn);
     return 0;
   }
-  return run_units_pipelined(c, N, bits, out, c->hBlocks, 0, (size_t)cnt, fl) ? (size_t)h.n : 0;
+  return run_units_pipelined(c, family, N, bits, out, c->hBlocks, 0, (size_t)cnt, fl) ? (size_t)h.n : 0;
 }
 
 // Many independent streams of one codec in ONE launch: raw and block_ streams are a single recurrence each (one
@@ -973,7 +993,7 @@ extern "C" size_t hsr_decode_batch(int family, int N, int bits, const uint8_t *i
     if (!grow(c->dBlocks, c->blocksCap, units.size())) return 0;
     std::stable_sort(units.begin(), units.end(), [](const hsr_block_t &a, const hsr_block_t &b) { return a.count > b.count; }); // longest first
     CU_TRY(cudaMemcpyAsync(c->dBlocks, units.data(), units.size() * sizeof(hsr_block_t), cudaMemcpyHostToDevice, c->sRun), return 0);
-    if (launch_units(N, bits, c->dIn, inLo, c->dOut, outLo, c->dBlocks, (uint32_t)units.size(), c->dCounters, c->sRun, dStreamStatus) < 0)
+    if (launch_units(family, N, bits, c->dIn, inLo, c->dOut, outLo, c->dBlocks, (uint32_t)units.size(), c->dCounters, c->sRun, dStreamStatus) < 0)
       return 0;
   }
   std::vector<uint32_t> status(4 + count);
@@ -1017,7 +1037,7 @@ extern "C" size_t hsr_decode_mt_multi(int N, int bits, const uint8_t *in, size_t
   if (!valid_codec(HSR_MT, N, bits)) { set_err("unsupported codec (N %d, bits %d)", N, bits); return 0; }
   if (deviceCount < 1) { set_err("deviceCount must be >= 1"); return 0; }
   Header h;
-  if (!read_header(N, in, inLength, outCapacity, &h)) return 0;
+  if (!read_header(HSR_MT, N, in, inLength, outCapacity, &h)) return 0;
   if (!out) { set_err("null output"); return 0; }
   const long cnt = hsr_mt_index(N, in, (size_t)h.compLen, nullptr, 0);
   if (cnt < 0) return 0;
@@ -1034,7 +1054,7 @@ extern "C" size_t hsr_decode_mt_multi(int N, int bits, const uint8_t *in, size_t
   for (int d = 0; d < deviceCount; d++) {
     workers.emplace_back([&, d]() {
       const int dev = devices ? devices[d] : d;
-      ok[d] = decode_units_from_host(dev, N, bits, in, out, units.data(), first[d], first[d + 1]);
+      ok[d] = decode_units_from_host(dev, HSR_MT, N, bits, in, out, units.data(), first[d], first[d + 1]);
       if (!ok[d]) errors[d] = g_err;
     });
   }

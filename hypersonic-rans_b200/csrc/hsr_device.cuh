@@ -391,7 +391,10 @@ struct WordRingTma {
 // Measured on B200 (profiles/r1/sweep_tma_ring_experiment.jsonl): the TMA ring is correct (all parity tests pass) but
 // 26-31 % SLOWER than the LDGSTS ring (571 vs 773 GB/s at mt_64x15, 838 vs 1220 at 10 bits): a 512-byte segment is
 // too small to amortise the mbarrier try_wait round trip per segment, and the extra live state costs registers
-// (92 in the packed 10-bit kernel). It stays available for larger-segment experiments; LDGSTS is the default.
+// (92 in the packed 10-bit kernel). A leaner two-buffer TMA ring (one pending bulk copy per warp, 16-byte granular
+// sizes) measured 726 GB/s against 903 for the two-buffer LDGSTS ring (profiles/r1/variants_ring_unroll.jsonl): small
+// bulk copies at ~3000 warps x 1 per 1.5 us are simply not what the TMA is good at. It stays available
+// (-DHSR_RING_TMA=1 -DHSR_RING2=0) for larger-segment experiments; LDGSTS is the default.
 #ifndef HSR_RING_TMA
 #define HSR_RING_TMA 0
 #endif

@@ -1,0 +1,222 @@
+// hsr_kernels_aux.cu — the two remaining 32-bit-state / 16-bit-word raw layouts of the reference's registry
+// (SURVEY.md §8f rank 4), on the same tables, word ring and unit records as the main kernels:
+//
+//   rANS32x16_16w        src/rANS32x16_16w.cpp:162-271: the raw format with 16 interleaved states. Lanes 0..15 of
+//                        the warp own the states, lanes 16..31 idle; byte position inside a row of 16 is
+//                        { 0-3, 8-11, 4-7, 12-15 } (:211). Words are handed out by the same ballot/popc prefix.
+//   rANS32x32_32blk_16w  src/rans32x32_32blk_16w.cpp:183-301: 32 states, but every state reads its words from its
+//                        OWN sub-stream (u32 blockSize[31] after the states, :223-231), so there is no shared
+//                        cursor at all: each lane walks a private read head through global memory (L1-resident,
+//                        one 128-byte line per lane, prefetched two lines ahead).
+//
+// Both are single recurrences (one warp per stream, latency-bound like every raw stream); throughput comes from
+// batches (hsr_decode_batch), which these kernels serve through the same persistent unit loop.
+#include "hsr_kernels.cuh"
+
+namespace hsr {
+
+// lane -> byte position inside a row of 16 (src/rANS32x16_16w.cpp:211)
+__device__ __forceinline__ uint32_t idx2idx16_lane(uint32_t l) { return (l & 3u) | ((l & 4u) << 1) | ((l & 8u) >> 1); }
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+struct UnitView {
+  const uint8_t *base, *end;
+  uint8_t *out;
+  uint64_t count;
+  uint32_t kind, tail, streamId;
+};
+
+__device__ __forceinline__ bool next_unit(const DecodeParams &p, uint32_t lane, UnitView *u)
+{
+  uint32_t b = 0;
+  if (lane == 0)
+    b = atomicAdd(p.counter, 1u);
+  b = __shfl_sync(kFull, b, 0);
+  if (b >= p.numBlocks)
+    return false;
+  const hsr_block_t *blk = p.blocks + b;
+  u->base = p.in + (__ldg(&blk->inOffset) - p.inBase);
+  u->end = p.in + (__ldg(&blk->inEnd) - p.inBase);
+  u->out = p.out + (__ldg(&blk->outOffset) - p.outBase);
+  u->count = __ldg(&blk->count);
+  u->kind = __ldg(&blk->kind);
+  u->tail = __ldg(&blk->tail);
+  u->streamId = __ldg(&blk->reserved);
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------- rANS32x16_16w
+
+template <int BITS>
+__device__ __forceinline__ void raw16_kernel_body(const DecodeParams &p)
+{
+  using L = WarpLayout<BITS, 32, TK_RANK>; // a row of 16 consumes at most 32 bytes: inside the 32-state ring's overlap
+  const uint32_t sw = declare_smem<L::kBytes>();
+  const uint32_t lane = lane_id();
+  const uint32_t ltMask = lanemask_lt();
+  const bool live = lane < 16u;
+  const uint32_t lanePos = idx2idx16_lane(lane & 15u);
+
+  Decoder<BITS, 32, TK_RANK> dec;
+  dec.init(sw);
+  Ring<L> ring;
+#if HSR_RING_TMA
+  ring.init(sw + L::kOffRing, sw + L::kOffBar, lane);
+#endif
+
+  UnitView u;
+  while (next_unit(p, lane, &u)) {
+    if (u.kind != 2u) { // only whole raw streams exist for this codec
+      raise(p.counter, p.streamStatus, u.streamId, HSR_ERR_INTERNAL, lane);
+      continue;
+    }
+    const uint8_t *countsPtr = u.base; // counts, then u32 states[16], then words (src/rANS32x16_16w.cpp:183-203)
+    const uint8_t *statesPtr = u.base + 512;
+    const uint8_t *words = u.base + 512 + 4 * 16;
+    const TableInfo info = build_tables<BITS, 32, TK_RANK>(sw, countsPtr, lane);
+    if (!info.ok) {
+      raise(p.counter, p.streamStatus, u.streamId, HSR_ERR_HIST, lane);
+      continue;
+    }
+    // idle lanes hold a state that never asks for a word; their lookups stay inside the tables
+    uint32_t x = live ? ldg_u32_a2(statesPtr + 4 * lane) : 0x80000000u;
+#if HSR_RING_TMA
+    ring.start(words, u.end, lane);
+#else
+    ring.start(sw + L::kOffRing, words, u.end, lane);
+#endif
+    const uint64_t rows = (u.count - u.tail) / 16u;
+    uint8_t *outLane = u.out + lanePos;
+    for (uint64_t r = 0; r < rows; r++) { // :213-238
+      ring.advance_if_needed(lane);
+      uint32_t t = x;
+      const uint32_t s = dec.template symbol_step_rank<false>(t);
+      if (live) {
+        x = t;
+        st_global_u8(outLane, s);
+      }
+      dec.renorm_masked(x, ring.wp, live, ltMask);
+      outLane += 16;
+    }
+    if (u.tail) { // :240-268
+      ring.advance_if_needed(lane);
+      const bool a = live && lanePos < u.tail;
+      uint32_t t = x;
+      const uint32_t s = dec.template symbol_step_rank<false>(t);
+      if (a) {
+        x = t;
+        st_global_u8(outLane, s);
+      }
+      dec.renorm_masked(x, ring.wp, a, ltMask);
+    }
+    ring.drain();
+    if (ring.cursor() > ring.glimit)
+      raise(p.counter, p.streamStatus, u.streamId, HSR_ERR_OVERRUN, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- rANS32x32_32blk_16w
+
+template <int BITS>
+__device__ __forceinline__ void blk32_kernel_body(const DecodeParams &p)
+{
+  using L = WarpLayout<BITS, 32, TK_RANK>;
+  const uint32_t sw = declare_smem<L::kBytes>();
+  const uint32_t lane = lane_id();
+  const uint32_t lanePos = idx2idx_lane(lane); // same permutation as rANS32x32_16w (src/rans32x32_32blk_16w.cpp:235)
+
+  Decoder<BITS, 32, TK_RANK> dec;
+  dec.init(sw);
+
+  UnitView u;
+  while (next_unit(p, lane, &u)) {
+    if (u.kind != 3u) {
+      raise(p.counter, p.streamStatus, u.streamId, HSR_ERR_INTERNAL, lane);
+      continue;
+    }
+    const uint8_t *countsPtr = u.base; // counts, u32 states[32], u32 blockSize[31], then the 32 sub-streams (:205-231)
+    const uint8_t *statesPtr = u.base + 512;
+    const uint8_t *sizesPtr = statesPtr + 4 * 32;
+    const uint8_t *data = sizesPtr + 4 * 31;
+    const TableInfo info = build_tables<BITS, 32, TK_RANK>(sw, countsPtr, lane);
+    if (!info.ok) {
+      raise(p.counter, p.streamStatus, u.streamId, HSR_ERR_HIST, lane);
+      continue;
+    }
+    uint32_t x = ldg_u32_a2(statesPtr + 4 * lane);
+
+    // pReadHead[j] = pReadHead[j - 1] + blockSize[j - 1] (:223-231): exclusive prefix sum of the 31 sizes
+    const uint64_t mine = lane < 31u ? (uint64_t)ldg_u32_a2(sizesPtr + 4 * lane) : 0ull;
+    uint64_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint64_t up = __shfl_up_sync(kFull, incl, d);
+      if (lane >= (uint32_t)d)
+        incl += up;
+    }
+    const uint64_t avail = (uint64_t)(u.end - data);
+    const uint64_t startOff = incl - mine;
+    if (__any_sync(kFull, startOff > avail)) { // a sub-stream would begin past the end of the stream
+      raise(p.counter, p.streamStatus, u.streamId, HSR_ERR_OVERRUN, lane);
+      continue;
+    }
+    const uint8_t *rd = data + startOff;
+    const uint8_t *const last = u.end - 2; // highest address a word may be read from
+    prefetch_l1(rd);
+    if (rd + 128 <= last) prefetch_l1(rd + 128);
+    bool bad = false;
+
+    auto renorm = [&](bool take) {
+      if (take && x < kConsumePoint16) {
+        uint32_t w = 0;
+        if (rd <= last)
+          w = ldg_u16(rd);
+        else
+          bad = true;
+        x = (x << 16) | w;
+        rd += 2;
+        if ((reinterpret_cast<uintptr_t>(rd) & 127u) == 0 && rd + 256 <= last)
+          prefetch_l1(rd + 256);
+      }
+    };
+
+    const uint64_t rows = (u.count - u.tail) / 32u;
+    uint8_t *outLane = u.out + lanePos;
+    for (uint64_t r = 0; r < rows; r++) { // :241-269
+      const uint32_t s = dec.template symbol_step_rank<false>(x);
+      st_global_u8(outLane, s);
+      renorm(true);
+      outLane += 32;
+    }
+    if (u.tail) { // :271-298
+      const bool a = lanePos < u.tail;
+      uint32_t t = x;
+      const uint32_t s = dec.template symbol_step_rank<false>(t);
+      if (a) {
+        x = t;
+        st_global_u8(outLane, s);
+      }
+      renorm(a);
+    }
+    if (__any_sync(kFull, bad))
+      raise(p.counter, p.streamStatus, u.streamId, HSR_ERR_OVERRUN, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- instantiation
+
+#define HSR_AUX_DEFINE(BITS)                                                                                          \
+  __global__ void __launch_bounds__(32, 16) raw16_b##BITS(DecodeParams p) { raw16_kernel_body<BITS>(p); }             \
+  __global__ void __launch_bounds__(32, 16) blk32_b##BITS(DecodeParams p) { blk32_kernel_body<BITS>(p); }
+
+HSR_AUX_DEFINE(10) HSR_AUX_DEFINE(11) HSR_AUX_DEFINE(12) HSR_AUX_DEFINE(13) HSR_AUX_DEFINE(14) HSR_AUX_DEFINE(15)
+
+#define HSR_AUX_ENTRY(name, BITS) { (const void *)name##BITS, nullptr, WarpLayout<BITS, 32, TK_RANK>::kBytes }
+
+extern const KernelEntry kKernelsRaw16[6] = { HSR_AUX_ENTRY(raw16_b, 10), HSR_AUX_ENTRY(raw16_b, 11), HSR_AUX_ENTRY(raw16_b, 12),
+                                              HSR_AUX_ENTRY(raw16_b, 13), HSR_AUX_ENTRY(raw16_b, 14), HSR_AUX_ENTRY(raw16_b, 15) };
+extern const KernelEntry kKernelsBlk32[6] = { HSR_AUX_ENTRY(blk32_b, 10), HSR_AUX_ENTRY(blk32_b, 11), HSR_AUX_ENTRY(blk32_b, 12),
+                                              HSR_AUX_ENTRY(blk32_b, 13), HSR_AUX_ENTRY(blk32_b, 14), HSR_AUX_ENTRY(blk32_b, 15) };
+
+} // namespace hsr

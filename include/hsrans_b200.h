@@ -29,8 +29,11 @@ extern "C" {
 typedef enum hsr_family {
   HSR_RAW = 0,   /* rANS32xN_16w        — one histogram, one recurrence   (src/rANS32x32_16w.cpp:130-158)            */
   HSR_BLOCK = 1, /* block_rANS32xN_16w  — in-band histograms, carried states (src/block_rANS32x32_16w_encode.cpp:262-285) */
-  HSR_MT = 2     /* mt_rANS32xN_16w     — independent blocks with state snapshots (src/mt_rANS32x64_16w_encode.cpp:266-298) */
+  HSR_MT = 2,    /* mt_rANS32xN_16w     — independent blocks with state snapshots (src/mt_rANS32x64_16w_encode.cpp:266-298) */
+  HSR_RAW32BLK = 3 /* rANS32x32_32blk_16w — raw header + u32 blockSize[31], one private word sub-stream per state
+                      (src/rans32x32_32blk_16w.cpp:147-176); stateCount must be 32 */
 } hsr_family_t;
+/* stateCount: 32 or 64 for every family; HSR_RAW also takes 16 = rANS32x16_16w (src/rANS32x16_16w.cpp:162-271). */
 
 /* ------------------------------------------------------------------------------------------------ general */
 
@@ -49,7 +52,8 @@ int hsr_set_option(const char *key, long value);
 long hsr_get_option(const char *key);
 
 /* Worst-case compressed size for n input bytes (the buffer size a harness must allocate).
- * Replaces rANS32x32_16w_capacity (src/rANS32x32_16w.cpp:10-13), block_rANS32x32_16w_capacity
+ * Replaces rANS32x32_16w_capacity (src/rANS32x32_16w.cpp:10-13), rANS32x16_16w_capacity (src/rANS32x16_16w.cpp:10-13),
+ * rANS32x32_32blk_16w_capacity (src/rans32x32_32blk_16w.cpp:10-13), block_rANS32x32_16w_capacity
  * (src/block_rANS32x32_16w_encode.cpp:47-54), mt_rANS32x64_16w_capacity (src/mt_rANS32x64_16w_encode.cpp:50-57). */
 size_t hsr_capacity(int family, int stateCount, size_t inputSize);
 
@@ -68,7 +72,8 @@ typedef struct hsr_batch_item {
 /* Host-pointer decode: H2D, index (mt_), kernels, D2H, synchronise. Replaces every function of type
  *   size_t f(const uint8_t *pInData, const size_t inLength, uint8_t *pOutData, const size_t outCapacity)
  * i.e. codec_info_t::decodeFunc (src/main.cpp:149): rANS32x32_16w_decode_scalar_<b> (src/rANS32x32_16w.cpp:161),
- * rANS32x64_16w_decode_scalar_<b> (src/rANS32x64_16w.cpp:168) and all their AVX variants,
+ * rANS32x64_16w_decode_scalar_<b> (src/rANS32x64_16w.cpp:168), rANS32x16_16w_decode_scalar_<b>
+ * (src/rANS32x16_16w.cpp:162), rANS32x32_32blk_16w_decode_scalar_<b> (src/rans32x32_32blk_16w.cpp:183) and all their AVX variants,
  * block_rANS32xNN_16w_decode_<b> (src/block_rANS32x32_16w_decode.cpp:165-193),
  * mt_rANS32xNN_16w_decode_<b> / _decode_mt_<b> (src/mt_rANS32x64_16w_decode.cpp:301-361).
  * Uses the current CUDA device (hsr_set_device). Re-entrant across threads; one internal context per device.
@@ -103,7 +108,7 @@ typedef struct hsr_block {
   uint64_t inEnd;     /* coded: byte offset one past the block's last word */
   uint64_t outOffset; /* first decoded byte of this unit */
   uint64_t count;     /* decoded bytes in this unit (coded: rows*N, plus `tail` extra lanes on the last one) */
-  uint32_t kind;      /* 0 coded mt_ layout, 1 fill, 2 coded raw layout */
+  uint32_t kind;      /* 0 coded mt_ layout, 1 fill, 2 coded raw layout, 3 coded raw 32blk layout */
   uint32_t symbol;    /* fill value for kind 1 */
   uint32_t tail;      /* 0, or the number of leftover symbols (< N) decoded after the last full row */
   uint32_t reserved;

@@ -15,8 +15,10 @@
 #include "hist.h"
 #include "simd_platform.h"
 #include "thread_pool.h"
+#include "rANS32x16_16w.h"
 #include "rANS32x32_16w.h"
 #include "rANS32x64_16w.h"
+#include "rans32x32_32blk_16w.h"
 #include "block_rANS32x32_16w.h"
 #include "block_rANS32x64_16w.h"
 #include "mt_rANS32x32_16w.h"
@@ -40,6 +42,14 @@ static const dec_fn raw_dec_avx2[2][6] = {
 static const dec_fn raw_dec_avx512[2][6] = {
   { rANS32x32_xmmShfl2_16w_decode_avx512_varC_10, rANS32x32_xmmShfl2_16w_decode_avx512_varC_11, rANS32x32_xmmShfl2_16w_decode_avx512_varC_12, nullptr, nullptr, nullptr },
   MIXED6(rANS32x64_xmmShfl2_16w_decode_avx512_varC, rANS32x64_xmmShfl2_16w_decode_avx512_varA) };
+// 16-state codec and the 32blk layout: `candidateForFastest` AVX2 rows of src/main.cpp:216-228 (xmmShfl varC /
+// varC2 for bits <= 12, xmmShfl varA / varA2 above)
+static const enc_hist_fn raw16_enc[6] = BITS6(rANS32x16_16w_encode_scalar);
+static const dec_fn raw16_dec_scalar[6] = BITS6(rANS32x16_16w_decode_scalar);
+static const dec_fn raw16_dec_avx2[6] = MIXED6(rANS32x16_xmmShfl_16w_decode_avx2_varC, rANS32x16_xmmShfl_16w_decode_avx2_varA);
+static const enc_hist_fn blk32_enc[6] = BITS6(rANS32x32_32blk_16w_encode_scalar);
+static const dec_fn blk32_dec_scalar[6] = BITS6(rANS32x32_32blk_16w_decode_scalar);
+static const dec_fn blk32_dec_avx2[6] = MIXED6(rANS32x32_32blk_16w_decode_avx2_varC2, rANS32x32_32blk_16w_decode_avx2_varA2);
 static const enc_fn block_enc[2][6] = { BITS6(block_rANS32x32_16w_encode), BITS6(block_rANS32x64_16w_encode) };
 static const dec_fn block_dec[2][6] = { BITS6(block_rANS32x32_16w_decode), BITS6(block_rANS32x64_16w_decode) };
 static const enc_fn mt_enc[2][6] = { BITS6(mt_rANS32x32_16w_encode), BITS6(mt_rANS32x64_16w_encode) };
@@ -49,11 +59,17 @@ static const dec_pool_fn mt_dec_pool[2][6] = { BITS6(mt_rANS32x32_16w_decode_mt)
 static thread_pool *g_pool = nullptr;
 static size_t g_pool_threads = 0;
 
-static bool ok(int family, int N, int bits) { return family >= 0 && family <= 2 && (N == 32 || N == 64) && bits >= 10 && bits <= 15; }
+static bool ok(int family, int N, int bits)
+{
+  if (bits < 10 || bits > 15) return false;
+  if (family == 0) return N == 16 || N == 32 || N == 64;
+  if (family == 3) return N == 32;
+  return (family == 1 || family == 2) && (N == 32 || N == 64);
+}
 
 extern "C" {
 
-enum { HSREF_RAW = 0, HSREF_BLOCK = 1, HSREF_MT = 2 };
+enum { HSREF_RAW = 0, HSREF_BLOCK = 1, HSREF_MT = 2, HSREF_RAW32BLK = 3 };
 // impl: 0 = scalar (raw) / CPU-dispatching decoder (block_, mt_ single thread)
 //       1 = fastest AVX2 raw decoder / same dispatching decoder
 //       2 = AVX-512 raw decoder (xmmShfl2) / same dispatching decoder
@@ -63,7 +79,8 @@ enum { HSREF_IMPL_SCALAR = 0, HSREF_IMPL_AVX2 = 1, HSREF_IMPL_AVX512 = 2, HSREF_
 size_t hsref_capacity(int family, int N, size_t n)
 {
   if (!ok(family, N, 10)) return 0;
-  if (family == HSREF_RAW) return N == 32 ? rANS32x32_16w_capacity(n) : rANS32x64_16w_capacity(n);
+  if (family == HSREF_RAW) return N == 16 ? rANS32x16_16w_capacity(n) : N == 32 ? rANS32x32_16w_capacity(n) : rANS32x64_16w_capacity(n);
+  if (family == HSREF_RAW32BLK) return rANS32x32_32blk_16w_capacity(n);
   if (family == HSREF_BLOCK) return N == 32 ? block_rANS32x32_16w_capacity(n) : block_rANS32x64_16w_capacity(n);
   return N == 32 ? mt_rANS32x32_16w_capacity(n) : mt_rANS32x64_16w_capacity(n);
 }
@@ -73,10 +90,11 @@ size_t hsref_encode(int family, int N, int bits, const uint8_t *in, size_t n, ui
 {
   if (!ok(family, N, bits)) return 0;
   const int s = N == 64, b = bits - 10;
-  if (family == HSREF_RAW) {
+  if (family == HSREF_RAW || family == HSREF_RAW32BLK) {
     hist_t hist;
     make_hist(&hist, in, n, (size_t)bits);
-    return raw_enc[s][b](in, n, out, cap, &hist);
+    if (family == HSREF_RAW32BLK) return blk32_enc[b](in, n, out, cap, &hist);
+    return N == 16 ? raw16_enc[b](in, n, out, cap, &hist) : raw_enc[s][b](in, n, out, cap, &hist);
   }
   return family == HSREF_BLOCK ? block_enc[s][b](in, n, out, cap) : mt_enc[s][b](in, n, out, cap);
 }
@@ -88,7 +106,7 @@ size_t hsref_encode_raw_with_hist(int N, int bits, const uint8_t *in, size_t n, 
   hist_t hist;
   memcpy(hist.symbolCount, symbolCount, sizeof(hist.symbolCount));
   if (!inplace_complete_hist(&hist, (size_t)bits)) return 0;
-  return raw_enc[N == 64][bits - 10](in, n, out, cap, &hist);
+  return N == 16 ? raw16_enc[bits - 10](in, n, out, cap, &hist) : raw_enc[N == 64][bits - 10](in, n, out, cap, &hist);
 }
 
 int hsref_pool_threads(void) { return (int)g_pool_threads; }
@@ -113,6 +131,14 @@ size_t hsref_decode(int family, int N, int bits, int impl, const uint8_t *in, si
 {
   if (!ok(family, N, bits)) return 0;
   const int s = N == 64, b = bits - 10;
+  if (family == HSREF_RAW32BLK || (family == HSREF_RAW && N == 16)) { // no AVX-512 decoders exist for these two
+    _DetectCPUFeatures();
+    const dec_fn *scalar = family == HSREF_RAW32BLK ? blk32_dec_scalar : raw16_dec_scalar;
+    const dec_fn *avx2 = family == HSREF_RAW32BLK ? blk32_dec_avx2 : raw16_dec_avx2;
+    if (impl == HSREF_IMPL_AVX2) return avx2Supported ? avx2[b](in, inLen, out, cap) : 0;
+    if (impl == HSREF_IMPL_AVX512) return 0;
+    return scalar[b](in, inLen, out, cap);
+  }
   if (family == HSREF_RAW) {
     _DetectCPUFeatures();
     if (impl == HSREF_IMPL_AVX2) return avx2Supported ? raw_dec_avx2[s][b](in, inLen, out, cap) : 0;

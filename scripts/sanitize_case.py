@@ -19,6 +19,18 @@ for key in sorted(z.files):
         ok = n == data.size and np.array_equal(out[:n], data)
         bad += not ok
         print(key, "table", table, "ok" if ok else "MISMATCH")
+z4 = np.load("tests/golden/golden_rank4.npz")  # rANS32x16_16w and rANS32x32_32blk_16w
+for key in sorted(z4.files):
+    if not key.startswith("stream/"):
+        continue
+    _, name, fam, states, bits = key.split("/")
+    if name not in ("multi", "tiny65", "tiny33", "small") or int(bits) not in (10, 12, 15):
+        continue
+    data = z4[f"in/{name}"]
+    n, out = pkg.decode(int(fam), int(states), int(bits), z4[key], data.size)
+    ok = n == data.size and np.array_equal(out[:n], data)
+    bad += not ok
+    print(key, "ok" if ok else "MISMATCH")
 cnt, cum = pkg.make_hist(z["in/multi"], 12)
 print("hist ok", np.array_equal(cnt, z["hist/multi/12"][0]))
 sys.exit(1 if bad else 0)

@@ -19,7 +19,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libhsrans_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libhsrans_ref.so")
-RAW, BLOCK, MT = 0, 1, 2
+RAW, BLOCK, MT, RAW32BLK = 0, 1, 2, 3
 IMPL_SCALAR, IMPL_AVX2, IMPL_AVX512, IMPL_POOL = 0, 1, 2, 3
 
 _oracle = None
@@ -201,4 +201,4 @@ def encode(family: int, states: int, bits: int, data) -> np.ndarray:
         return ref_encode(family, states, bits, data)
     if family == RAW:
         return oracle_encode_raw(states, bits, data)
-    raise RuntimeError("block_/mt_ streams need oracle/_ref (the reference encoders) or the golden fixtures")
+    raise RuntimeError("block_/mt_/32blk streams need oracle/_ref (the reference encoders) or the golden fixtures")

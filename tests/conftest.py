@@ -28,6 +28,13 @@ def golden():
     return {k: z[k] for k in z.files}
 
 
+@pytest.fixture(scope="session")
+def golden_rank4():
+    """rANS32x16_16w and rANS32x32_32blk_16w vectors (tests/golden/make_golden_rank4.py)"""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "golden_rank4.npz"))
+    return {k: z[k] for k in z.files}
+
+
 def golden_stream_cases(golden):
     """[(name, family, states, bits, stream, expected_return, input)]"""
     cases = []

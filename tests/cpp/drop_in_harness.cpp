@@ -20,6 +20,7 @@ struct entry_t { const char *name; decodeFunc func; };
 static const entry_t decoders[] = {
   ROWS(cuda_rANS32x32_16w_decode), ROWS(cuda_rANS32x64_16w_decode), ROWS(cuda_block_rANS32x32_16w_decode),
   ROWS(cuda_block_rANS32x64_16w_decode), ROWS(cuda_mt_rANS32x32_16w_decode), ROWS(cuda_mt_rANS32x64_16w_decode),
+  ROWS(cuda_rANS32x16_16w_decode), ROWS(cuda_rANS32x32_32blk_16w_decode),
 };
 
 static std::vector<uint8_t> slurp(const char *path)

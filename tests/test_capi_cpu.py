@@ -121,6 +121,14 @@ def test_synth_is_deterministic_and_zipf_shaped(pkg):
 def test_codec_registry_mirrors_reference_rows(pkg):
     names = {c.name for c in pkg.CODECS}
     assert "rANS32x64 16w 12 (raw)" in names and "rANS32x32 16w 10" in names and "rANS32x64 16w 15 mt" in names
-    assert len(pkg.CODECS) == 36
+    assert "rANS32x16 16w 13 (raw)" in names and "rANS32x32 32blk 16w 15 (raw)" in names  # main.cpp:216-228
+    assert len(pkg.CODECS) == 48
     c = pkg.find_codec(pkg.HSR_MT, 64, 15)
     assert c.symbol == "mt_rANS32x64_16w_decode_15"
+    assert pkg.find_codec(pkg.HSR_RAW32BLK, 32, 11).symbol == "rANS32x32_32blk_16w_decode_scalar_11"
+
+
+def test_capacity_of_the_16_state_and_32blk_layouts(pkg):
+    for n in (0, 1, 100, 12345, 100_000_000):
+        assert pkg.capacity(pkg.HSR_RAW, 16, n) == ck.oracle_capacity(ck.RAW, 16, n) == n + 16 + 512 + 64 + 16
+        assert pkg.capacity(pkg.HSR_RAW32BLK, 32, n) == ck.oracle_capacity(ck.RAW32BLK, 32, n) == n + 32 + 512 + 256 + 16

@@ -91,3 +91,71 @@ def test_oracle_vs_compiled_reference_on_fresh_inputs():
             assert np.array_equal(out_or[:n], out_ref[:n]) and np.array_equal(out_or[:n], data)
         for bits in (10, 13, 15):
             assert all(np.array_equal(a, b) for a, b in zip(ck.oracle_make_hist(data, bits), ck.ref_make_hist(data, bits)))
+
+
+# ---------------------------------------------------------------------------- rANS32x16_16w / rANS32x32_32blk_16w
+
+def test_oracle_decodes_every_rank4_golden_stream(golden_rank4):
+    cases = golden_stream_cases(golden_rank4)
+    assert len(cases) >= 90
+    seen = set()
+    for name, fam, states, bits, stream, ret, data in cases:
+        assert (fam, states) in ((ck.RAW, 16), (ck.RAW32BLK, 32))
+        seen.add((fam, states, bits))
+        n, out = ck.oracle_decode(fam, states, bits, stream, data.size)
+        assert n == ret == data.size, (name, fam, states, bits, n, ret)
+        assert np.array_equal(out[:n], data), (name, fam, states, bits)
+        assert ck.oracle_decode(fam, states, bits, stream, data.size - 1)[0] == 0      # capacity one byte short
+        assert ck.oracle_decode(fam, states, bits, stream[:-1], data.size)[0] == 0     # inLength < compressedLength
+    assert len(seen) == 12
+
+
+def test_oracle_16_state_encoder_twin_is_byte_identical(golden_rank4):
+    hit = 0
+    for name, fam, states, bits, stream, ret, data in golden_stream_cases(golden_rank4):
+        if fam != ck.RAW:
+            continue
+        assert np.array_equal(ck.oracle_encode_raw(16, bits, data), stream), (name, bits)
+        hit += 1
+    assert hit >= 40
+
+
+def test_idx2idx16_closed_form():
+    table16 = [0x00, 0x01, 0x02, 0x03, 0x08, 0x09, 0x0A, 0x0B, 0x04, 0x05, 0x06, 0x07, 0x0C, 0x0D, 0x0E, 0x0F]  # src/rANS32x16_16w.cpp:211
+    lib = ck.oracle()
+    lib.hsro_idx2idx16.restype = lib.hsro_idx2idx.restype
+    lib.hsro_idx2idx16.argtypes = lib.hsro_idx2idx.argtypes
+    assert [lib.hsro_idx2idx16(j) for j in range(16)] == table16
+
+
+def test_oracle_32blk_rejects_sub_streams_past_the_end(golden_rank4):
+    stream = golden_rank4["stream/small/3/32/12"].copy()
+    n = golden_rank4["in/small"].size
+    sizes = 16 + 512 + 128
+    bad = stream.copy()
+    bad[sizes:sizes + 4] = np.frombuffer(np.uint32(stream.size).tobytes(), np.uint8)  # first sub-stream "longer" than the file
+    assert ck.oracle_decode(ck.RAW32BLK, 32, 12, bad, n)[0] == 0
+    bad = stream.copy(); bad[16 + 9] ^= 0x10                                           # histogram no longer sums to 2^12
+    assert ck.oracle_decode(ck.RAW32BLK, 32, 12, bad, n)[0] == 0
+    assert ck.oracle_decode(ck.RAW32BLK, 32, 12, stream[:16 + 512 + 4 * 63 - 1], n)[0] == 0  # shorter than the fixed header
+
+
+@pytest.mark.skipif(not ck.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+def test_oracle_vs_compiled_reference_rank4_fresh_inputs():
+    rng = np.random.default_rng(77)
+    for trial in range(8):
+        n = int(rng.integers(64, 300_000))
+        s = float(rng.choice([0.0, 0.7, 1.0, 1.6, 2.5]))
+        p = 1.0 / np.arange(1, 257) ** s
+        p /= p.sum()
+        data = rng.permutation(256).astype(np.uint8)[rng.choice(256, n, p=p)]
+        for fam, states in ((ck.RAW, 16), (ck.RAW32BLK, 32)):
+            bits = int(rng.integers(10, 16))
+            try:
+                stream = ck.ref_encode(fam, states, bits, data)
+            except ck.RefEncoderOverflow:
+                continue
+            n_ref, out_ref = ck.ref_decode(fam, states, bits, stream, n, ck.IMPL_AVX2)
+            n_or, out_or = ck.oracle_decode(fam, states, bits, stream, n)
+            assert n_ref == n_or == n, (fam, states, bits, n, n_ref, n_or)
+            assert np.array_equal(out_or[:n], out_ref[:n]) and np.array_equal(out_or[:n], data)
