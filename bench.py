@@ -215,7 +215,8 @@ def other_configs(pkg, torch, a, heavy):
     data = pkg.synth_zipf(n, 1.0, seed=42, segment_bytes=0)
     out = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
     for label, fam, states, bits in (("rANS32x64_16w_12_raw", 0, 64, 12), ("block_rANS32x32_16w_10", 1, 32, 10),
-                                     ("rANS32x32_16w_11_raw", 0, 32, 11)):
+                                     ("rANS32x32_16w_11_raw", 0, 32, 11), ("rANS32x16_16w_12_raw", 0, 16, 12),
+                                     ("rANS32x32_32blk_16w_15_raw", 3, 32, 15)):
         stream = ck.ref_encode(fam, states, bits, data)
         ps = pkg.PreparedStream.upload(fam, states, bits, stream)
         st = torch.cuda.current_stream().cuda_stream
