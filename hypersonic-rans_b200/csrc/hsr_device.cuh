@@ -199,6 +199,8 @@ struct WordRing {
     __syncwarp();
   }
 
+  __device__ __forceinline__ void start_wait() const {}
+
   // call once per row, before any word of the row is read
   __device__ __forceinline__ void advance_if_needed(uint32_t lane)
   {
@@ -263,6 +265,11 @@ struct WordRing2 {
     __syncwarp(); // every lane is done with whatever lived in the ring before
     issue();
     issue();
+  }
+  // start() only posts the first two segments; call this before the first word is read (the table build of the
+  // block sits between the two, so its global loads and the ring's overlap)
+  __device__ __forceinline__ void start_wait()
+  {
     cp_async_wait<1>();
     __syncwarp();
   }
@@ -366,6 +373,8 @@ struct WordRingTma {
     wp = buf(g0) + (uint32_t)(a & 15);
     wlimit = buf(g0) + L::kStride;
   }
+
+  __device__ __forceinline__ void start_wait() const {}
 
   __device__ __forceinline__ void advance_if_needed(uint32_t lane)
   {
@@ -477,8 +486,29 @@ __device__ __forceinline__ TableInfo build_tables(uint32_t smemWarp, const uint8
   }
   __syncwarp();
 
-  // prefix of start counts over the groups, 32 groups per step (lane <-> group: conflict-free)
+  // prefix of start counts over the groups. 128 groups per step where the table has that many: lane l owns groups
+  // 4l .. 4l+3 (one conflict-free 16-byte load and store), so one warp scan serves four groups per lane — the
+  // shuffles of that scan share the shared-memory data pipe with every lookup of the other resident warps.
   uint32_t carry = 0;
+  if constexpr (L::kGroups >= 128) {
+#pragma unroll 2
+    for (uint32_t g0 = 0; g0 < (uint32_t)L::kGroups; g0 += 128u) {
+      const uint32_t a = sGrp + (g0 + 4u * lane) * 4u;
+      const uint4 bm = lds_v4(a);
+      const uint32_t c0 = __popc(bm.x), c1 = __popc(bm.y), c2 = __popc(bm.z), c3 = __popc(bm.w);
+      const uint32_t tot = c0 + c1 + c2 + c3;
+      uint32_t scan = tot;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(kFull, scan, d);
+        if (lane >= (uint32_t)d)
+          scan += up;
+      }
+      const uint32_t e0 = carry + scan - tot, e1 = e0 + c0, e2 = e1 + c1, e3 = e2 + c2;
+      sts_v4(a, make_uint4((e0 << 16) | bm.x, (e1 << 16) | bm.y, (e2 << 16) | bm.z, (e3 << 16) | bm.w));
+      carry += __shfl_sync(kFull, scan, 31);
+    }
+  } else
 #pragma unroll 2
   for (uint32_t g0 = 0; g0 < (uint32_t)L::kGroups; g0 += 32u) {
     const uint32_t a = sGrp + (g0 + lane) * 4u;

@@ -63,13 +63,16 @@ __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
   ring.init(sw + L::kOffRing, sw + L::kOffBar, lane);
 #endif
 
+  // the next unit is claimed while the current one decodes, so the atomic's round trip is off the path
+  uint32_t claimed = 0;
+  if (lane == 0)
+    claimed = atomicAdd(p.counter, 1u);
   for (;;) {
-    uint32_t b = 0;
-    if (lane == 0)
-      b = atomicAdd(p.counter, 1u);
-    b = __shfl_sync(kFull, b, 0);
+    const uint32_t b = __shfl_sync(kFull, claimed, 0);
     if (b >= p.numBlocks)
       break;
+    if (lane == 0)
+      claimed = atomicAdd(p.counter, 1u);
 
     const hsr_block_t *blk = p.blocks + b;
     const uint64_t inOffset = __ldg(&blk->inOffset);
@@ -92,22 +95,25 @@ __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
     const uint8_t *countsPtr = kind == 0u ? base + 4 * N : base;
     const uint8_t *words = base + 4 * N + 512;
 
-    const TableInfo info = build_tables<BITS, N, TK>(sw, countsPtr, lane);
-    if (!info.ok) {
-      raise(p.counter, p.streamStatus, streamId, HSR_ERR_HIST, lane);
-      continue;
-    }
-
+    // states and the first word segments are requested before the table build, whose own loads they overlap
     uint32_t x0 = ldg_u32_a2(statesPtr + 4 * lane);
     uint32_t x1 = 0;
     if constexpr (N == 64)
       x1 = ldg_u32_a2(statesPtr + 4 * (lane + 32));
-
 #if HSR_RING_TMA
     ring.start(words, end, lane);
 #else
     ring.start(sw + L::kOffRing, words, end, lane);
 #endif
+
+    const TableInfo info = build_tables<BITS, N, TK>(sw, countsPtr, lane);
+    if (!info.ok) {
+      ring.start_wait();
+      ring.drain();
+      raise(p.counter, p.streamStatus, streamId, HSR_ERR_HIST, lane);
+      continue;
+    }
+    ring.start_wait();
 
     const uint64_t rows = (count - tailCount) / N;
     uint8_t *outLane = out + lanePos;
@@ -197,6 +203,7 @@ __device__ __forceinline__ void block_stream_decode(const BlockStreamParams &p, 
 #else
       ring.start(sRing, in + pos, streamEnd, lane);
 #endif
+      ring.start_wait();
       dec.rows(info, x0, x1, ring, outBase + i + lanePos, rows, lane, ltMask);
       ring.drain();
       if (ring.cursor() > ring.glimit) {
@@ -223,6 +230,7 @@ __device__ __forceinline__ void block_stream_decode(const BlockStreamParams &p, 
 #else
     ring.start(sRing, in + pos, streamEnd, lane);
 #endif
+    ring.start_wait();
     dec.tail(x0, x1, ring, outBase + i + lanePos, lanePos, (uint32_t)(n - i), lane, ltMask);
     ring.drain();
   }

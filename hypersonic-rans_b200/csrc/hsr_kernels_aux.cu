@@ -86,6 +86,7 @@ __device__ __forceinline__ void raw16_kernel_body(const DecodeParams &p)
 #else
     ring.start(sw + L::kOffRing, words, u.end, lane);
 #endif
+    ring.start_wait();
     const uint64_t rows = (u.count - u.tail) / 16u;
     uint8_t *outLane = u.out + lanePos;
     for (uint64_t r = 0; r < rows; r++) { // :213-238
