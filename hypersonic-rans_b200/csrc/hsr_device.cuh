@@ -47,6 +47,11 @@
 #ifndef HSR_RING2
 #define HSR_RING2 1
 #endif
+//   HSR_QUAD_STORE  1: four half-rows of decoded bytes leave as one 32-bit store per lane after a 4x4 byte transpose
+//                   inside each lane quad (see rows_impl); 0: one byte store per lane and half-row
+#ifndef HSR_QUAD_STORE
+#define HSR_QUAD_STORE 0
+#endif
 
 namespace hsr {
 
@@ -120,6 +125,7 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uin
 
 __device__ __forceinline__ uint4 lds_v4(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 __device__ __forceinline__ void st_global_v4(uint8_t *p, uint4 v) { asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+__device__ __forceinline__ void st_global_u32(uint8_t *p, uint32_t v) { asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void st_global_u8(uint8_t *p, uint32_t v) { asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------- layout
@@ -652,6 +658,54 @@ struct Decoder {
         __syncwarp();
         outLane += 512;
       }
+    }
+#endif
+#if HSR_QUAD_STORE
+    // Quad-transposed stores: four half-rows of symbols (2 rows at N = 64, 4 rows at N = 32) are packed into one
+    // register per lane and transposed inside each group of four lanes (two SHFL.BFLY + two PRMT), after which lane
+    // 4m + h holds four CONSECUTIVE output bytes of half-row h — lanes 4m .. 4m+3 own byte positions p .. p+3 of a
+    // half-row (idx2idx keeps the low two lane bits) — and one 32-bit store per lane replaces four byte stores:
+    // 2 x 1.1 + 1.5 cycles of the shared-memory/LSU data pipe instead of 4 x 1.4 (profiles/r1/ubench_lsu.jsonl).
+    if ((reinterpret_cast<uintptr_t>(outLane - idx2idx_lane(lane)) & 3) == 0) {
+      constexpr uint32_t kGroupRows = N == 64 ? 2 : 4;
+      const uint32_t selA = (lane & 1u) ? 0x3715u : 0x6240u, selB = (lane & 2u) ? 0x3276u : 0x5410u;
+      uint8_t *outQuad = outLane - idx2idx_lane(lane) + 32u * (lane & 3u) + idx2idx_lane(lane & ~3u);
+#pragma unroll(kRowUnroll / kGroupRows > 0 ? kRowUnroll / kGroupRows : 1)
+      for (; r + kGroupRows <= rows; r += kGroupRows) {
+        uint32_t s[4];
+#pragma unroll
+        for (uint32_t t = 0; t < kGroupRows; t++) {
+          ring.advance_if_needed(lane);
+          if constexpr (N == 64) {
+            if constexpr (kMode == 0) {
+              s[2 * t] = symbol_step_packed(x0);
+              s[2 * t + 1] = symbol_step_packed(x1);
+            } else {
+              s[2 * t] = symbol_step_rank<kMode == 1>(x0);
+              s[2 * t + 1] = symbol_step_rank<kMode == 1>(x1);
+            }
+            renorm(x0, ring.wp, ltMask);
+            renorm(x1, ring.wp, ltMask);
+          } else {
+            if constexpr (kMode == 0)
+              s[t] = symbol_step_packed(x0);
+            else
+              s[t] = symbol_step_rank<kMode == 1>(x0);
+            renorm(x0, ring.wp, ltMask);
+          }
+        }
+        uint32_t a;
+        if constexpr (kMode == 0) { // the packed entry carries freq above the symbol byte: pick bytes
+          a = __byte_perm(__byte_perm(s[0], s[1], 0x0040), __byte_perm(s[2], s[3], 0x0040), 0x5410);
+        } else {                    // ranks / symbols are < 256: multiply-adds on the FMA pipe
+          a = (s[3] * 256u + s[2]) * 65536u + (s[1] * 256u + s[0]);
+        }
+        const uint32_t b = __byte_perm(a, __shfl_xor_sync(kFull, a, 1), selA);
+        const uint32_t c = __byte_perm(b, __shfl_xor_sync(kFull, b, 2), selB);
+        st_global_u32(outQuad, c);
+        outQuad += 128;
+      }
+      outLane += (size_t)r * N;
     }
 #endif
 #pragma unroll kRowUnroll
