@@ -301,6 +301,27 @@ def other_configs(pkg, torch, a, heavy):
                                           "compressed_bytes": int(comp), "blocks": int(ps.units), "round_trip_bit_exact": ok,
                                           "decode_GBps_of_this_stream": round(n / dec_ms / 1e6, 2)}
         ps.free()
+        # the same bytes through the device block-split policy (hsr_encode_mt_policy_device, 256 KiB max blocks)
+        comp_p = pkg.encode_mt_policy_device(a.states, a.bits, d_in.data_ptr(), n, d_out.data_ptr(), bound, 0, st)
+        times_p = []
+        for _ in range(3):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            comp_p = pkg.encode_mt_policy_device(a.states, a.bits, d_in.data_ptr(), n, d_out.data_ptr(), bound, 0, st)
+            torch.cuda.synchronize(); times_p.append(time.perf_counter() - t0)
+        ps = pkg.PreparedStream.from_device(2, a.states, a.bits, d_out.data_ptr(), comp_p)
+        ps.decode_async(out3.data_ptr(), n, st)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            ps.decode_async(out3.data_ptr(), n, st)
+        e1.record()
+        torch.cuda.synchronize()
+        ok_p = comp_p > 0 and ps.status() == 0 and bool(torch.equal(out3[:n], d_in))
+        res[f"device_encoder_policy_{shape}"] = {"encode_GBps": round(n / min(times_p) / 1e9, 2), "encode_ms": round(min(times_p) * 1e3, 3),
+                                                 "compressed_bytes": int(comp_p), "blocks": int(ps.units), "max_block_bytes": 262144,
+                                                 "round_trip_bit_exact": ok_p,
+                                                 "decode_GBps_of_this_stream": round(n / (e0.elapsed_time(e1) / 5) / 1e6, 2)}
+        ps.free()
         if shape == "pw64k":
             hist = torch.zeros(256, dtype=torch.int32, device="cuda")
             counts = torch.zeros(((n + 65535) // 65536, 256), dtype=torch.int16, device="cuda")

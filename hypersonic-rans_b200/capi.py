@@ -66,6 +66,8 @@ SIGNATURES = {
     "hsr_encode_mt": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]),
     "hsr_encode_mt_device": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
     "hsr_encode_mt_bound": (C.c_size_t, [C.c_int, C.c_size_t, C.c_size_t]),
+    "hsr_encode_mt_policy": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "hsr_encode_mt_policy_device": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
     "hsr_synth_zipf": (C.c_int, [C.c_void_p, C.c_size_t, C.c_double, C.c_uint64, C.c_size_t]),
 }
 
@@ -300,6 +302,24 @@ def encode_mt(state_count: int, bits: int, data, block_size: int = 0) -> np.ndar
     if n == 0:
         raise HsrError(f"hsr_encode_mt failed: {last_error()}")
     return out[:n].copy()
+
+
+def encode_mt_policy(state_count: int, bits: int, data, max_block_size: int = 0) -> np.ndarray:
+    """Device mt_ encoder with the block-split policy decided on the device (hsr_encode_mt_policy)."""
+    src = _as_u8(data)
+    bound = lib().hsr_encode_mt_bound(state_count, src.size, 0)
+    if bound == 0:
+        raise HsrError("hsr_encode_mt_bound: unsupported arguments")
+    out = np.empty(bound, np.uint8)
+    n = lib().hsr_encode_mt_policy(state_count, bits, _ptr(src), src.size, _ptr(out), bound, max_block_size)
+    if n == 0:
+        raise HsrError(f"hsr_encode_mt_policy failed: {last_error()}")
+    return out[:n].copy()
+
+
+def encode_mt_policy_device(state_count: int, bits: int, d_in: int, length: int, d_out: int, out_capacity: int, max_block_size: int = 0,
+                            cuda_stream: int = 0) -> int:
+    return lib().hsr_encode_mt_policy_device(state_count, bits, d_in, length, d_out, out_capacity, max_block_size, cuda_stream)
 
 
 def encode_mt_device(state_count: int, bits: int, d_in: int, length: int, d_out: int, out_capacity: int, block_size: int = 0,

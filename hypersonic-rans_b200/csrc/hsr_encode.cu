@@ -31,10 +31,14 @@ namespace hsr {
 
 struct EncPlan {
   uint64_t n;          // input bytes
-  uint32_t blockSize;  // symbols per block (multiple of N)
+  uint32_t blockSize;  // symbols per block (multiple of N); fixed-size mode
   uint32_t numBlocks;
   uint64_t lastStart;  // first symbol of the last block (it also owns the < N ragged symbols at the end)
-  uint64_t slotBytes;  // scratch bytes per block: worst case one word per symbol
+  uint64_t slotBytes;  // scratch bytes per block: worst case one word per symbol (fixed-size mode)
+  // policy mode (hsr_encode_mt_policy*): variable blocks from the device block-split pass
+  const uint64_t *starts; // numBlocks + 1 symbol offsets, or nullptr in fixed-size mode
+  const uint32_t *kinds;  // per block: bit 0 = single-symbol run, bits 8..15 = its symbol
+  uint32_t slotPad;       // scratch slack per block in policy mode
 };
 
 struct EncBlockMeta {
@@ -43,8 +47,18 @@ struct EncBlockMeta {
   uint32_t states[64];
 };
 
-__device__ __forceinline__ uint64_t block_begin(const EncPlan &pl, uint32_t k) { return (uint64_t)k * pl.blockSize; }
-__device__ __forceinline__ uint64_t block_end(const EncPlan &pl, uint32_t k) { return k + 1 == pl.numBlocks ? pl.n : (uint64_t)(k + 1) * pl.blockSize; }
+__device__ __forceinline__ uint64_t block_begin(const EncPlan &pl, uint32_t k) { return pl.starts ? pl.starts[k] : (uint64_t)k * pl.blockSize; }
+__device__ __forceinline__ uint64_t block_end(const EncPlan &pl, uint32_t k)
+{
+  if (pl.starts) return pl.starts[k + 1];
+  return k + 1 == pl.numBlocks ? pl.n : (uint64_t)(k + 1) * pl.blockSize;
+}
+__device__ __forceinline__ bool block_is_run(const EncPlan &pl, uint32_t k) { return pl.kinds && (pl.kinds[k] & 1u); }
+// end of block k's scratch slot (its words grow downward from there)
+__device__ __forceinline__ uint64_t slot_end(const EncPlan &pl, uint32_t k)
+{
+  return pl.starts ? 2 * pl.starts[k + 1] + (uint64_t)(k + 1) * pl.slotPad : (uint64_t)(k + 1) * pl.slotBytes;
+}
 
 // ---------------------------------------------------------------------------------------------- per-block histograms
 
@@ -56,6 +70,7 @@ __global__ void __launch_bounds__(kSegWarps * 32) enc_hist_kernel(const uint8_t 
   __shared__ uint16_t sCapped[kSegWarps][256];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   for (uint32_t k = blockIdx.x * kSegWarps + warp; k < pl.numBlocks; k += gridDim.x * kSegWarps) {
+    if (block_is_run(pl, k)) continue;
     const uint64_t begin = block_begin(pl, k), end = block_end(pl, k);
     warp_observe(data, begin, end, sHist[warp], lane);
     warp_normalize(sHist[warp], end - begin, bits, sCapped[warp], sHist[warp], counts + (uint64_t)k * 256, lane); // :209-210
@@ -90,6 +105,10 @@ __global__ void __launch_bounds__(32, 32) enc_block_kernel(const uint8_t *__rest
     k = __shfl_sync(kFull, k, 0);
     if (k >= pl.numBlocks)
       break;
+    if (block_is_run(pl, k)) { // single-symbol run: 8 header bytes, no words, no states
+      if (lane == 0) meta[k].wordBytes = 0;
+      continue;
+    }
 
     // table: lane owns symbols 8l .. 8l+7
     {
@@ -133,7 +152,7 @@ __global__ void __launch_bounds__(32, 32) enc_block_kernel(const uint8_t *__rest
     const uint32_t tailLen = (uint32_t)(len % N);
     const uint8_t *src = in + begin;
 
-    uint8_t *slotEnd = scratch + (uint64_t)(k + 1) * pl.slotBytes; // words grow downward from here
+    uint8_t *slotEnd = scratch + slot_end(pl, k); // words grow downward from here
     uint8_t *wp = slotEnd;
     uint32_t x0 = kConsumePoint16, x1 = kConsumePoint16; // fresh states (:222-223)
 
@@ -200,7 +219,8 @@ __global__ void __launch_bounds__(32, 32) enc_block_kernel(const uint8_t *__rest
 // ---------------------------------------------------------------------------------------------- offsets
 
 // offsets[k] = stream offset of block k's u64 size field; offsets[numBlocks] = total compressed length
-__global__ void __launch_bounds__(1024) enc_scan_kernel(const EncBlockMeta *meta, uint32_t numBlocks, uint32_t headerBytes, uint64_t *offsets)
+__global__ void __launch_bounds__(1024) enc_scan_kernel(const EncBlockMeta *meta, uint32_t numBlocks, uint32_t headerBytes, const uint32_t *kinds,
+                                                        uint64_t *offsets)
 {
   __shared__ uint64_t sWarp[32];
   __shared__ uint64_t sCarry;
@@ -209,7 +229,8 @@ __global__ void __launch_bounds__(1024) enc_scan_kernel(const EncBlockMeta *meta
   __syncthreads();
   for (uint32_t base = 0; base < numBlocks; base += 1024) {
     const uint32_t k = base + tid;
-    const uint64_t v = k < numBlocks ? (uint64_t)headerBytes + meta[k].wordBytes : 0;
+    uint64_t v = 0;
+    if (k < numBlocks) v = (kinds && (kinds[k] & 1u)) ? 8 : (uint64_t)headerBytes + meta[k].wordBytes;
     uint64_t incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -255,6 +276,13 @@ __global__ void __launch_bounds__(256) enc_assemble_kernel(EncPlan pl, const uin
       const uint64_t v = tid < 4 ? pl.n : offsets[pl.numBlocks];
       st_u16(out + 2 * tid, (uint32_t)(v >> (16 * (tid & 3))));
     }
+    if (block_is_run(pl, k)) { // :300-305: size | 1 << 63 | symbol << 54, nothing else
+      if (tid < 4) {
+        const uint64_t v = (block_end(pl, k) - block_begin(pl, k)) | (1ull << 63) | ((uint64_t)((pl.kinds[k] >> 8) & 0xffu) << 54);
+        st_u16(dst + 2 * tid, (uint32_t)(v >> (16 * tid)));
+      }
+      continue;
+    }
     if (tid < 4) { // u64 symbol count of the block (:296-297)
       const uint64_t size = block_end(pl, k) - block_begin(pl, k);
       st_u16(dst + 2 * tid, (uint32_t)(size >> (16 * tid)));
@@ -267,10 +295,137 @@ __global__ void __launch_bounds__(256) enc_assemble_kernel(EncPlan pl, const uin
       st_u16(dst + 16 + 2 * i, meta[k].states[i >> 1] >> (16 * (i & 1)));
     for (uint32_t i = tid; i < 256; i += blockDim.x)
       st_u16(dst + 16 + 4 * N + 2 * i, counts[(uint64_t)k * 256 + i]);
-    const uint8_t *src = scratch + (uint64_t)(k + 1) * pl.slotBytes - wordBytes;
+    const uint8_t *src = scratch + slot_end(pl, k) - wordBytes;
     uint8_t *wdst = dst + kHeader;
     for (uint32_t i = tid; i < wordBytes / 2; i += blockDim.x)
       st_u16(wdst + 2 * i, *reinterpret_cast<const uint16_t *>(src + 2 * i));
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------- block-split policy
+
+// the reference grows a block over further MinBlockSize (64 KiB) segments while coding a segment
+// with the block's histogram costs less than giving it its own histogram plus half a header (_CanExtendHist,
+// src/mt_rANS32x64_16w_encode.cpp:61-136, the log2f cost sums of :101-135 and the threshold of :98-99), and turns
+// stretches of one repeated byte into 8-byte run blocks (:171-187, :300-305). The same decisions are taken here on the
+// device from per-segment byte counts: one warp per chunk of `segsPerChunk` segments walks its segments FORWARD (the
+// reference walks backward from the end of the file; any split decodes) and marks where blocks start.
+// Differences, deliberately: blocks never span a chunk (max block size = chunk size, so the split itself is parallel
+// and the result keeps >= n / chunk independent blocks for the GPU decoder), the costs use the raw segment counts
+// instead of a second, normalised histogram per candidate, and runs are found at segment granularity.
+constexpr uint32_t kSegBytes = 65536; // MinBlockSize for every bit width (:34-45)
+
+__global__ void __launch_bounds__(kSegWarps * 32) enc_seg_count_kernel(const uint8_t *data, uint64_t n, uint32_t numSegs, uint32_t *segCounts)
+{
+  __shared__ uint32_t sHist[kSegWarps][256];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (uint32_t t = blockIdx.x * kSegWarps + warp; t < numSegs; t += gridDim.x * kSegWarps) {
+    const uint64_t begin = (uint64_t)t * kSegBytes, end = t + 1 == numSegs ? n : begin + kSegBytes;
+    warp_observe(data, begin, end, sHist[warp], lane);
+    for (int i = lane; i < 256; i += 32) segCounts[(uint64_t)t * 256 + i] = sHist[warp][i];
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+  return v;
+}
+
+// flags[t]: 0 = segment t continues the open block, 1 = starts a coded block, 2 | symbol << 8 = starts a run block
+__global__ void __launch_bounds__(32) enc_policy_kernel(const uint32_t *segCounts, uint64_t n, uint32_t numSegs, uint32_t segsPerChunk, int bits,
+                                                        uint32_t headerBytes, uint32_t *flags)
+{
+  const uint32_t lane = threadIdx.x & 31u;
+  const float replacePoint = (float)((((uint32_t)1 << bits) * (bits == 15 ? 50u : 500u)) >> 12); // HistReplaceMul, :17-29,98-99
+  for (uint32_t chunk = blockIdx.x; (uint64_t)chunk * segsPerChunk < numSegs; chunk += gridDim.x) {
+    const uint32_t t0 = chunk * segsPerChunk, t1 = min(numSegs, t0 + segsPerChunk);
+    float oldLog[8];   // log2 of the open block's first-segment counts (absent symbols count 1, IsSafeHist :193-203)
+    float oldLogTotal = 0.f;
+    int open = 0;      // 0 none, 1 coded, 2 run
+    uint32_t runSym = 0;
+    for (uint32_t t = t0; t < t1; t++) {
+      const uint64_t begin = (uint64_t)t * kSegBytes, end = t + 1 == numSegs ? n : begin + kSegBytes;
+      const uint32_t len = (uint32_t)(end - begin);
+      uint32_t c[8], maxC = 0, zeros = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        c[i] = segCounts[(uint64_t)t * 256 + lane + 32 * i];
+        maxC = max(maxC, c[i]);
+        zeros += c[i] == 0;
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        maxC = max(maxC, __shfl_xor_sync(kFull, maxC, d));
+        zeros += __shfl_xor_sync(kFull, zeros, d);
+      }
+      const bool isRun = maxC == len;
+      uint32_t sym = 0;
+      if (isRun) {
+        uint32_t mine = 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if (c[i] == len) mine = lane + 32 * i;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mine = min(mine, __shfl_xor_sync(kFull, mine, d));
+        sym = mine;
+      }
+      uint32_t flag;
+      if (isRun) {
+        flag = (open == 2 && sym == runSym) ? 0u : (2u | (sym << 8));
+        open = 2;
+        runSym = sym;
+      } else {
+        bool extend = false;
+        if (open == 1) { // :101-135
+          const float logLen = __log2f((float)len);
+          float before = 0.f, after = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+            if (c[i]) {
+              before += (float)(c[i] - 1u) * (oldLogTotal - oldLog[i]);
+              after += (float)c[i] * (logLen - __log2f((float)c[i]));
+            }
+          before = warp_sum(before);
+          after = warp_sum(after) + (float)headerBytes * 0.5f;
+          extend = (before - after) < replacePoint;
+        }
+        flag = extend ? 0u : 1u;
+        if (!extend) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) oldLog[i] = __log2f((float)max(c[i], 1u));
+          oldLogTotal = __log2f((float)(len + zeros));
+        }
+        open = 1;
+      }
+      if (lane == 0) flags[t] = flag;
+    }
+  }
+}
+
+// flags -> block table: starts[b] (symbol offsets, starts[numBlocks] = n), kinds[b]; result[0] = numBlocks
+__global__ void __launch_bounds__(32) enc_blocks_kernel(const uint32_t *flags, uint32_t numSegs, uint64_t n, uint64_t *starts, uint32_t *kinds,
+                                                        uint32_t *result)
+{
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t count = 0;
+  for (uint32_t base = 0; base < numSegs; base += 32) {
+    const uint32_t t = base + lane;
+    const uint32_t f = t < numSegs ? flags[t] : 0u;
+    const uint32_t m = __ballot_sync(kFull, f != 0u);
+    if (f) {
+      const uint32_t b = count + __popc(m & lanemask_lt());
+      starts[b] = (uint64_t)t * kSegBytes;
+      kinds[b] = ((f & 2u) ? 1u : 0u) | (f & 0xff00u);
+    }
+    count += __popc(m);
+  }
+  if (lane == 0) {
+    starts[count] = n;
+    result[0] = count;
   }
 }
 
@@ -301,6 +456,7 @@ bool make_plan(int N, uint64_t n, size_t blockSize, EncPlan *pl)
   if (blockSize == 0) blockSize = 65536;
   if (blockSize % (size_t)N || blockSize > (1u << 25) || n < (uint64_t)N) return false; // max block size of the reference, :47-48
   pl->n = n;
+  pl->starts = nullptr; pl->kinds = nullptr; pl->slotPad = 0;
   pl->blockSize = (uint32_t)blockSize;
   uint64_t blocks = (n + blockSize - 1) / blockSize;
   // the last block must hold at least one full row: a shorter remainder rides along as the previous block's ragged tail
@@ -323,7 +479,26 @@ struct EncScratch {
   uint64_t *dOffsets = nullptr;
   uint32_t *dCounter = nullptr;
   size_t blocksCap = 0, scratchCap = 0;
+  // block-split policy pass
+  uint32_t *dSegCounts = nullptr, *dFlags = nullptr, *dKinds = nullptr, *dResult = nullptr;
+  uint64_t *dStarts = nullptr;
+  size_t segsCap = 0;
   std::mutex mu;
+
+  bool ensure_policy(size_t segs)
+  {
+    if (segs > segsCap) {
+      cudaFree(dSegCounts); cudaFree(dFlags); cudaFree(dKinds); cudaFree(dStarts);
+      dSegCounts = dFlags = dKinds = nullptr; dStarts = nullptr; segsCap = 0;
+      const size_t want = segs + segs / 8 + 16;
+      if (cudaMalloc(&dSegCounts, want * 1024) != cudaSuccess || cudaMalloc(&dFlags, want * 4) != cudaSuccess ||
+          cudaMalloc(&dKinds, want * 4) != cudaSuccess || cudaMalloc(&dStarts, (want + 1) * 8) != cudaSuccess)
+        return false;
+      segsCap = want;
+    }
+    if (!dResult && cudaMalloc(&dResult, 16) != cudaSuccess) return false;
+    return true;
+  }
 
   bool ensure(size_t blocks, size_t scratchBytes)
   {
@@ -397,7 +572,7 @@ extern "C" size_t hsr_encode_mt_device(int N, int bits, const void *dInV, size_t
   const unsigned gridE = (unsigned)std::min<uint64_t>(pl.numBlocks, (uint64_t)sms * 32);
   if (N == 32) launch_encode_n<32>(bits, dIn, pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dCounter, gridE, st);
   else launch_encode_n<64>(bits, dIn, pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dCounter, gridE, st);
-  enc_scan_kernel<<<1, 1024, 0, st>>>(sc.dMeta, pl.numBlocks, 16 + 4 * (uint32_t)N + 512, sc.dOffsets);
+  enc_scan_kernel<<<1, 1024, 0, st>>>(sc.dMeta, pl.numBlocks, 16 + 4 * (uint32_t)N + 512, nullptr, sc.dOffsets);
   uint64_t total = 0;
   if (cudaMemcpyAsync(&total, sc.dOffsets + pl.numBlocks, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
     (void)cudaGetLastError();
@@ -408,6 +583,89 @@ extern "C" size_t hsr_encode_mt_device(int N, int bits, const void *dInV, size_t
   else enc_assemble_kernel<64><<<gridH, 256, 0, st>>>(pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dOffsets, dOut);
   if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return 0;
   return (size_t)total;
+}
+
+// Block-split policy on the device. Same stream format; blocks are whole numbers of 64 KiB
+// segments chosen by the reference's cost model (see enc_policy_kernel), at most maxBlockSize bytes each (0 = 256 KiB;
+// a multiple of 65536, at most 2^25 = the reference's MaxBlockSize), and stretches of one repeated byte become
+// 8-byte run blocks. Every block is still encoded from fresh states, so the result stays independent GPU work.
+extern "C" size_t hsr_encode_mt_policy_device(int N, int bits, const void *dInV, size_t length, void *dOutV, size_t outCapacity,
+                                              size_t maxBlockSize, void *cudaStream)
+{
+  if (!(N == 32 || N == 64) || bits < 10 || bits > 15 || !dInV || !dOutV || length < (size_t)N) return 0;
+  if (maxBlockSize == 0) maxBlockSize = 4 * (size_t)kSegBytes;
+  if (maxBlockSize % kSegBytes || maxBlockSize > (1u << 25)) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(cudaStream);
+  const uint8_t *dIn = static_cast<const uint8_t *>(dInV);
+  uint8_t *dOut = static_cast<uint8_t *>(dOutV);
+  uint64_t segs = (length + kSegBytes - 1) / kSegBytes;
+  if (segs > 1 && length - (segs - 1) * kSegBytes < (uint64_t)N) segs -= 1; // a shorter remainder rides along with the last segment
+  if (segs > 0x7fffffffull) return 0;
+  const uint32_t numSegs = (uint32_t)segs, segsPerChunk = (uint32_t)(maxBlockSize / kSegBytes);
+  const uint32_t slotPad = (2u * (uint32_t)N + 31u) & ~15u;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  EncScratch &sc = *scratch_for_device(dev);
+  std::lock_guard<std::mutex> lock(sc.mu);
+  if (!sc.ensure(numSegs, 2 * length + (size_t)numSegs * slotPad + 64) || !sc.ensure_policy(numSegs)) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  const uint32_t headerBytes = 16 + 4 * (uint32_t)N + 512;
+  cudaMemsetAsync(sc.dCounter, 0, 16, st);
+  const unsigned gridS = (unsigned)std::min<uint64_t>((numSegs + kSegWarps - 1) / kSegWarps, (uint64_t)sms * 16);
+  enc_seg_count_kernel<<<gridS, kSegWarps * 32, 0, st>>>(dIn, length, numSegs, sc.dSegCounts);
+  const uint32_t chunks = (numSegs + segsPerChunk - 1) / segsPerChunk;
+  enc_policy_kernel<<<std::min<uint32_t>(chunks, (uint32_t)sms * 32u), 32, 0, st>>>(sc.dSegCounts, length, numSegs, segsPerChunk, bits, headerBytes, sc.dFlags);
+  enc_blocks_kernel<<<1, 32, 0, st>>>(sc.dFlags, numSegs, length, sc.dStarts, sc.dKinds, sc.dResult);
+  uint32_t numBlocks = 0;
+  if (cudaMemcpyAsync(&numBlocks, sc.dResult, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess ||
+      numBlocks == 0 || numBlocks > numSegs) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  EncPlan pl{};
+  pl.n = length; pl.blockSize = 0; pl.numBlocks = numBlocks; pl.lastStart = 0; pl.slotBytes = 0;
+  pl.starts = sc.dStarts; pl.kinds = sc.dKinds; pl.slotPad = slotPad;
+  const unsigned gridH = (unsigned)std::min<uint64_t>(numBlocks, (uint64_t)sms * 8);
+  const unsigned gridB = (unsigned)std::min<uint64_t>((numBlocks + kSegWarps - 1) / kSegWarps, (uint64_t)sms * 16);
+  enc_hist_kernel<<<gridB, kSegWarps * 32, 0, st>>>(dIn, pl, bits, sc.dCounts);
+  const unsigned gridE = (unsigned)std::min<uint64_t>(numBlocks, (uint64_t)sms * 32);
+  if (N == 32) launch_encode_n<32>(bits, dIn, pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dCounter, gridE, st);
+  else launch_encode_n<64>(bits, dIn, pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dCounter, gridE, st);
+  enc_scan_kernel<<<1, 1024, 0, st>>>(sc.dMeta, numBlocks, headerBytes, sc.dKinds, sc.dOffsets);
+  uint64_t total = 0;
+  if (cudaMemcpyAsync(&total, sc.dOffsets + numBlocks, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  if (total > outCapacity) return 0;
+  if (N == 32) enc_assemble_kernel<32><<<gridH, 256, 0, st>>>(pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dOffsets, dOut);
+  else enc_assemble_kernel<64><<<gridH, 256, 0, st>>>(pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dOffsets, dOut);
+  if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return 0;
+  return (size_t)total;
+}
+
+// Host-pointer form with the reference's encoder signature plus the maximum block size.
+extern "C" size_t hsr_encode_mt_policy(int N, int bits, const uint8_t *pInData, size_t length, uint8_t *pOutData, size_t outCapacity,
+                                       size_t maxBlockSize)
+{
+  if (!pInData || !pOutData) return 0;
+  const size_t bound = hsr_encode_mt_bound(N, length, 0); // fixed 64 KiB blocks are the worst case for header bytes
+  if (bound == 0) return 0;
+  uint8_t *dIn = nullptr, *dOut = nullptr;
+  size_t result = 0;
+  if (cudaMalloc(&dIn, length + 16) == cudaSuccess && cudaMalloc(&dOut, bound) == cudaSuccess &&
+      cudaMemcpy(dIn, pInData, length, cudaMemcpyHostToDevice) == cudaSuccess) {
+    const size_t total = hsr_encode_mt_policy_device(N, bits, dIn, length, dOut, bound, maxBlockSize, nullptr);
+    if (total && total <= outCapacity && cudaMemcpy(pOutData, dOut, total, cudaMemcpyDeviceToHost) == cudaSuccess)
+      result = total;
+  }
+  (void)cudaGetLastError();
+  cudaFree(dIn);
+  cudaFree(dOut);
+  return result;
 }
 
 // Host-pointer encode with the reference's encoder signature (src/mt_rANS32x64_16w.h:9-14) plus the block size.

@@ -197,6 +197,16 @@ size_t hsr_encode_mt(int stateCount, int bits, const uint8_t *pInData, size_t le
 /* Device-pointer form; dOut should hold hsr_encode_mt_bound() bytes. Synchronises cudaStream once. */
 size_t hsr_encode_mt_device(int stateCount, int bits, const void *dIn, size_t length, void *dOut, size_t outCapacity, size_t blockSize,
                             void *cudaStream);
+/* The same producer with the reference's block-split POLICY decided on the device: blocks are
+ * whole numbers of 64 KiB segments, grown while coding the next segment with the block's histogram costs less than
+ * a histogram of its own plus half a header (_CanExtendHist, src/mt_rANS32x64_16w_encode.cpp:61-136), and stretches
+ * of one repeated byte become 8-byte run blocks (:171-187, :300-305). maxBlockSize (0 = 262144; a multiple of 65536,
+ * at most 2^25) bounds a block and is also the grain at which the split runs in parallel, so the stream keeps at
+ * least length / maxBlockSize independent blocks for the GPU decoder. hsr_encode_mt_bound(N, length, 0) bounds the size. */
+size_t hsr_encode_mt_policy(int stateCount, int bits, const uint8_t *pInData, size_t length, uint8_t *pOutData, size_t outCapacity,
+                            size_t maxBlockSize);
+size_t hsr_encode_mt_policy_device(int stateCount, int bits, const void *dIn, size_t length, void *dOut, size_t outCapacity,
+                                   size_t maxBlockSize, void *cudaStream);
 /* Hard upper bound of the stream size for `length` input bytes (one 16-bit word per symbol + headers). */
 size_t hsr_encode_mt_bound(int stateCount, size_t length, size_t blockSize);
 
