@@ -136,3 +136,21 @@ def test_rank4_20mb_round_trip(gpu):
     for fam, states, bits in ((ck.RAW, 16, 11), (ck.RAW32BLK, 32, 15)):
         stream = ck.ref_encode(fam, states, bits, data)
         _check(gpu, fam, states, bits, stream, data, "20 MB")
+
+
+@pytest.mark.skipif(not ck.have_ref(), reason="stream production for these codecs needs oracle/_ref")
+def test_32blk_streams_the_reference_encoder_corrupted_decode_like_the_reference_decoder(gpu):
+    """The reference's 32blk encoder overflows a state's word region on incompressible input and then fails its own
+    round trip (see tests/test_oracle_golden.py); the GPU must reproduce what the reference DEcoder makes of it."""
+    seen = 0
+    for seed, bits, n in ((0, 10, 50_000), (2, 10, 50_000), (1, 15, 50_000), (0, 12, 50_000)):
+        data = np.random.default_rng(seed).integers(0, 256, n).astype(np.uint8)
+        try:
+            stream = ck.ref_encode(ck.RAW32BLK, 32, bits, data)
+        except ck.RefEncoderOverflow:
+            continue
+        rn, ro = ck.ref_decode(ck.RAW32BLK, 32, bits, stream, n)
+        got_n, got = gpu.decode(ck.RAW32BLK, 32, bits, stream, n)
+        assert got_n == rn == n and np.array_equal(got[:n], ro[:n]), (seed, bits, n)
+        seen += not np.array_equal(ro[:n], data)
+    assert seen >= 1

@@ -166,17 +166,9 @@ def test_oracle_equals_reference_decoder_on_streams_its_32blk_encoder_corrupts()
     """Reference bug pinned as behaviour: rANS32x32_32blk_16w_encode gives every state a region of (n + 32) / 32 bytes
     (src/rans32x32_32blk_16w.cpp:47-56); a sub-stream that needs more overwrites its neighbour's words, and the
     reference then fails its own round trip. What counts for parity is the DEcoder's output on that stream."""
-    rng = np.random.default_rng(3)
     broken = 0
-    for case in range(120):
-        bits = int(rng.integers(10, 16))
-        n = int(rng.integers(3000, 400_000))
-        s = float(rng.choice([0.0, 0.3, 0.8, 1.0, 1.3, 2.0, 3.5]))
-        p = 1.0 / np.arange(1, 257) ** s
-        p /= p.sum()
-        data = rng.permutation(256).astype(np.uint8)[rng.choice(256, n, p=p)]
-        lo = int(rng.integers(0, n // 2)); hi = int(rng.integers(lo, n))
-        data[lo:hi] = int(rng.integers(0, 256))     # a long single-symbol run skews the histogram against the rest
+    for seed, bits, n in ((0, 10, 50_000), (2, 10, 50_000), (1, 15, 50_000), (0, 12, 50_000), (3, 10, 77_777), (4, 10, 31_000)):
+        data = np.random.default_rng(seed).integers(0, 256, n).astype(np.uint8)   # incompressible: ~8.0x bits per symbol
         try:
             stream = ck.ref_encode(ck.RAW32BLK, 32, bits, data)
         except ck.RefEncoderOverflow:
@@ -184,6 +176,6 @@ def test_oracle_equals_reference_decoder_on_streams_its_32blk_encoder_corrupts()
         rn, ro = ck.ref_decode(ck.RAW32BLK, 32, bits, stream, n)
         on, oo = ck.oracle_decode(ck.RAW32BLK, 32, bits, stream, n)
         assert rn == on == n
-        assert np.array_equal(oo[:n], ro[:n]), (case, bits, n)
+        assert np.array_equal(oo[:n], ro[:n]), (seed, bits, n)
         broken += not np.array_equal(ro[:n], data)
     assert broken >= 1   # the quirk exists in this build of the reference
