@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(1024) enc_scan_kernel(const EncBlockMeta *meta
 __device__ __forceinline__ void st_u16(uint8_t *p, uint32_t v) { *reinterpret_cast<uint16_t *>(p) = (uint16_t)v; }
 
 template <int N>
-__global__ void __launch_bounds__(256) enc_assemble_kernel(EncPlan pl, const uint16_t *counts, const uint8_t *scratch, const EncBlockMeta *meta,
+__global__ void __launch_bounds__(256, 8) enc_assemble_kernel(EncPlan pl, const uint16_t *counts, const uint8_t *scratch, const EncBlockMeta *meta,
                                                            const uint64_t *offsets, uint8_t *out)
 {
   const uint32_t tid = threadIdx.x;

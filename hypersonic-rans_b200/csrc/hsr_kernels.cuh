@@ -63,15 +63,22 @@ __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
   ring.init(sw + L::kOffRing, sw + L::kOffBar, lane);
 #endif
 
-  // the next unit is claimed while the current one decodes, so the atomic's round trip is off the path
+  // While plenty of units remain, the next one is claimed as soon as the current one is known, so the atomic's round
+  // trip hides behind the decode. Near the end (less than two rounds of the grid left) units are claimed only when a
+  // warp is free: a warp that sat on a pre-claimed unit would leave others idle — with as many units as CTAs (a
+  // batch of raw streams) the early CTAs would take two units each and the late ones none.
   uint32_t claimed = 0;
+  bool ahead = true;
   if (lane == 0)
     claimed = atomicAdd(p.counter, 1u);
   for (;;) {
+    if (!ahead && lane == 0)
+      claimed = atomicAdd(p.counter, 1u);
     const uint32_t b = __shfl_sync(kFull, claimed, 0);
     if (b >= p.numBlocks)
       break;
-    if (lane == 0)
+    ahead = (uint64_t)b + 2ull * gridDim.x < p.numBlocks;
+    if (ahead && lane == 0)
       claimed = atomicAdd(p.counter, 1u);
 
     const hsr_block_t *blk = p.blocks + b;
