@@ -6,8 +6,8 @@
 //                        { 0-3, 8-11, 4-7, 12-15 } (:211). Words are handed out by the same ballot/popc prefix.
 //   rANS32x32_32blk_16w  src/rans32x32_32blk_16w.cpp:183-301: 32 states, but every state reads its words from its
 //                        OWN sub-stream (u32 blockSize[31] after the states, :223-231), so there is no shared
-//                        cursor at all: each lane walks a private read head through global memory (L1-resident,
-//                        one 128-byte line per lane, prefetched two lines ahead).
+//                        cursor at all: each lane walks a private read head through global memory, its next two
+//                        words always preloaded into registers (L1-resident lines, prefetched two lines ahead).
 //
 // Both are single recurrences (one warp per stream, latency-bound like every raw stream); throughput comes from
 // batches (hsr_decode_batch), which these kernels serve through the same persistent unit loop.
@@ -17,8 +17,6 @@ namespace hsr {
 
 // lane -> byte position inside a row of 16 (src/rANS32x16_16w.cpp:211)
 __device__ __forceinline__ uint32_t idx2idx16_lane(uint32_t l) { return (l & 3u) | ((l & 4u) << 1) | ((l & 8u) >> 1); }
-
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 struct UnitView {
   const uint8_t *base, *end;
@@ -89,15 +87,15 @@ __device__ __forceinline__ void raw16_kernel_body(const DecodeParams &p)
     ring.start_wait();
     const uint64_t rows = (u.count - u.tail) / 16u;
     uint8_t *outLane = u.out + lanePos;
+#pragma unroll 4
     for (uint64_t r = 0; r < rows; r++) { // :213-238
       ring.advance_if_needed(lane);
-      uint32_t t = x;
-      const uint32_t s = dec.template symbol_step_rank<false>(t);
-      if (live) {
-        x = t;
+      const uint32_t s = dec.template symbol_step_rank<false>(x);
+      if (live)
         st_global_u8(outLane, s);
-      }
-      dec.renorm_masked(x, ring.wp, live, ltMask);
+      else
+        x = 0x80000000u; // idle lanes: pinned above the consume point, so the unmasked hand-out skips them
+      dec.renorm(x, ring.wp, ltMask);
       outLane += 16;
     }
     if (u.tail) { // :240-268
@@ -162,28 +160,35 @@ __device__ __forceinline__ void blk32_kernel_body(const DecodeParams &p)
       raise(p.counter, p.streamStatus, u.streamId, HSR_ERR_OVERRUN, lane);
       continue;
     }
+    // Each lane always holds its next TWO words in registers. A renormalisation takes the first, promotes the second
+    // and requests the one after it — in straight-line code that every lane executes every row (re-reading the same
+    // word when none was taken). The address of that load depends on this row's decision, but its value is only
+    // needed at the lane's renormalisation after the next one, so the load (an L1 hit: the lane's 128-byte line is
+    // prefetched two lines ahead) never sits on the symbol -> renormalise -> symbol chain.
+    // Everything below is selects and predicated instructions: a lone warp pays ~100 cycles for every divergent
+    // branch region in its loop (measured: 254 cycles per row this way, 344-474 with branches around the refill).
     const uint8_t *rd = data + startOff;
     const uint8_t *const last = u.end - 2; // highest address a word may be read from
-    prefetch_l1(rd);
-    if (rd + 128 <= last) prefetch_l1(rd + 128);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(rd));
+    if (rd + 128 <= last) asm volatile("prefetch.global.L1 [%0];" ::"l"(rd + 128));
+    uint32_t w0 = rd <= last ? ldg_u16(rd) : 0u;
+    uint32_t w1 = rd + 2 <= last ? ldg_u16(rd + 2) : 0u;
     bool bad = false;
 
-    auto renorm = [&](bool take) {
-      if (take && x < kConsumePoint16) {
-        uint32_t w = 0;
-        if (rd <= last)
-          w = ldg_u16(rd);
-        else
-          bad = true;
-        x = (x << 16) | w;
-        rd += 2;
-        if ((reinterpret_cast<uintptr_t>(rd) & 127u) == 0 && rd + 256 <= last)
-          prefetch_l1(rd + 256);
-      }
+    auto renorm = [&](bool may) {
+      const bool take = may && x < kConsumePoint16;
+      x = take ? ((x << 16) | w0) : x;
+      bad = bad || (take && rd > last); // the word came from beyond the end of the stream (read as zero)
+      w0 = take ? w1 : w0;
+      rd += take ? 2 : 0;
+      if (take && (reinterpret_cast<uintptr_t>(rd) & 127u) == 0 && rd + 256 <= last)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(rd + 256));
+      w1 = rd + 2 <= last ? ldg_u16(rd + 2) : 0u;
     };
 
     const uint64_t rows = (u.count - u.tail) / 32u;
     uint8_t *outLane = u.out + lanePos;
+#pragma unroll 2
     for (uint64_t r = 0; r < rows; r++) { // :241-269
       const uint32_t s = dec.template symbol_step_rank<false>(x);
       st_global_u8(outLane, s);
