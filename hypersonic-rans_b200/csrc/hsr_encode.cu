@@ -407,25 +407,44 @@ __global__ void __launch_bounds__(32) enc_policy_kernel(const uint32_t *segCount
 }
 
 // flags -> block table: starts[b] (symbol offsets, starts[numBlocks] = n), kinds[b]; result[0] = numBlocks
-__global__ void __launch_bounds__(32) enc_blocks_kernel(const uint32_t *flags, uint32_t numSegs, uint64_t n, uint64_t *starts, uint32_t *kinds,
-                                                        uint32_t *result)
+__global__ void __launch_bounds__(1024) enc_blocks_kernel(const uint32_t *flags, uint32_t numSegs, uint64_t n, uint64_t *starts, uint32_t *kinds,
+                                                          uint32_t *result)
 {
-  const uint32_t lane = threadIdx.x & 31u;
-  uint32_t count = 0;
-  for (uint32_t base = 0; base < numSegs; base += 32) {
-    const uint32_t t = base + lane;
+  __shared__ uint32_t sWarp[32];
+  __shared__ uint32_t sBase, sTotal;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (tid == 0) sBase = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < numSegs; base += 1024) {
+    const uint32_t t = base + tid;
     const uint32_t f = t < numSegs ? flags[t] : 0u;
     const uint32_t m = __ballot_sync(kFull, f != 0u);
+    if (lane == 0) sWarp[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+      const uint32_t v = sWarp[lane];
+      uint32_t incl = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(kFull, incl, d);
+        if (lane >= (uint32_t)d) incl += up;
+      }
+      sWarp[lane] = incl - v;
+      if (lane == 31) sTotal = incl;
+    }
+    __syncthreads();
     if (f) {
-      const uint32_t b = count + __popc(m & lanemask_lt());
+      const uint32_t b = sBase + sWarp[warp] + __popc(m & lanemask_lt());
       starts[b] = (uint64_t)t * kSegBytes;
       kinds[b] = ((f & 2u) ? 1u : 0u) | (f & 0xff00u);
     }
-    count += __popc(m);
+    __syncthreads();
+    if (tid == 0) sBase += sTotal;
+    __syncthreads();
   }
-  if (lane == 0) {
-    starts[count] = n;
-    result[0] = count;
+  if (tid == 0) {
+    starts[sBase] = n;
+    result[0] = sBase;
   }
 }
 
@@ -618,7 +637,7 @@ extern "C" size_t hsr_encode_mt_policy_device(int N, int bits, const void *dInV,
   enc_seg_count_kernel<<<gridS, kSegWarps * 32, 0, st>>>(dIn, length, numSegs, sc.dSegCounts);
   const uint32_t chunks = (numSegs + segsPerChunk - 1) / segsPerChunk;
   enc_policy_kernel<<<std::min<uint32_t>(chunks, (uint32_t)sms * 32u), 32, 0, st>>>(sc.dSegCounts, length, numSegs, segsPerChunk, bits, headerBytes, sc.dFlags);
-  enc_blocks_kernel<<<1, 32, 0, st>>>(sc.dFlags, numSegs, length, sc.dStarts, sc.dKinds, sc.dResult);
+  enc_blocks_kernel<<<1, 1024, 0, st>>>(sc.dFlags, numSegs, length, sc.dStarts, sc.dKinds, sc.dResult);
   uint32_t numBlocks = 0;
   if (cudaMemcpyAsync(&numBlocks, sc.dResult, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess ||
       numBlocks == 0 || numBlocks > numSegs) {
