@@ -24,7 +24,8 @@ class Block(C.Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhsrans_b200.so")
+    # HSRANS_B200_LIB lets the A/B scripts run the test-suite against a build variant (scripts/build_variant.sh)
+    return os.environ.get("HSRANS_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhsrans_b200.so")
 
 
 _lib = None
