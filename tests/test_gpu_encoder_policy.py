@@ -105,3 +105,16 @@ def test_policy_device_pointer_form_and_limits(gpu):
     assert gpu.encode_mt_policy_device(64, 15, d_in.data_ptr(), n, d_out.data_ptr(), bound, 1 << 26, st) == 0      # above the reference's MaxBlockSize
     assert gpu.encode_mt_policy_device(48, 15, d_in.data_ptr(), n, d_out.data_ptr(), bound, 0, st) == 0
     assert gpu.encode_mt_policy_device(64, 15, d_in.data_ptr(), n, d_out.data_ptr(), 1000, 0, st) == 0             # output too small
+
+
+def test_ragged_run_at_the_end_and_odd_lengths(gpu):
+    for states, bits, n in ((64, 14, 323_457), (32, 10, 65536 * 3 + 1), (64, 15, 65536 + 65), (32, 12, 65536 * 2 + 31)):
+        data = gpu.synth_zipf(n, 1.0, seed=n % 97, segment_bytes=65536)
+        data[n // 3:] = 0x2A          # a run that reaches the (unaligned) end of the input
+        stream = _roundtrip(gpu, states, bits, data, max_block=4 * 65536)
+        fills = [b for b in _blocks(gpu, states, stream) if b.kind == 1]
+        if n - n // 3 >= 2 * 65536:
+            assert fills and sum(int(b.count) for b in fills) >= ((n - n // 3) // 65536 - 1) * 65536
+        data2 = gpu.synth_zipf(n, 1.0, seed=5, segment_bytes=0)
+        data2[: n // 2] = 0x00        # and one at the beginning
+        _roundtrip(gpu, states, bits, data2, max_block=8 * 65536)
