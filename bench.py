@@ -271,6 +271,26 @@ def other_configs(pkg, torch, a, heavy):
         ps.free()
         del out2
 
+    # BASELINE config 4's low-parallelism case: the reference encoder merges stationary (iid) data into ~32 MiB blocks
+    # (src/mt_rANS32x64_16w_encode.cpp:207-213), i.e. ~62 independent warps of work per GB whatever the GPU
+    data = pkg.synth_zipf(a.size, a.zipf, seed=42, segment_bytes=0)
+    stream = ck.ref_encode(2, a.states, a.bits, data)
+    ps = pkg.PreparedStream.upload(2, a.states, a.bits, stream)
+    out4 = torch.empty(a.size + 64, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ps.decode_async(out4.data_ptr(), a.size, st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ps.decode_async(out4.data_ptr(), a.size, st)
+    e1.record()
+    torch.cuda.synchronize()
+    res["mt_iid_reference_encoded"] = {"gpu_decoded_GBps": round(a.size / e0.elapsed_time(e1) / 1e6, 2), "gpu_ms": round(e0.elapsed_time(e1), 3),
+                                       "blocks": int(ps.units), "bit_exact": ps.status() == 0 and bool(np.array_equal(out4[:a.size].cpu().numpy(), data)),
+                                       "note": "one warp per block: parallelism is a property of the stream"}
+    ps.free()
+    del out4
+
     # device-side producer (hsr_encode_mt_device) and the histogram kernels, on the same 1 GB of bytes
     n = a.size
     for shape, seg in (("pw64k", 65536), ("iid", 0)):
