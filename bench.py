@@ -435,12 +435,20 @@ def main():
             ps.decode_async(out_dev.data_ptr(), n, cur)
             ev[k + 1].record()
         barrier()
+        # The timed region lasts ~20 ms, about one NVML query: keep the same launches going (untimed) under the same
+        # sampler so the clock record covers a stretch of this exact load, not a single reading
+        t_probe = time.time()
+        while not (a.kernel_only or a.headline_only) and time.time() - t_probe < 0.25:  # not under the profiler
+            for _ in range(10):
+                ps.decode_async(out_dev.data_ptr(), n, cur)
+            torch.cuda.synchronize()
     total_ms = ev[0].elapsed_time(ev[a.steps])
     step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(a.steps)]
     total_ms = max_over_ranks(total_ms)
     ms_per_step = total_ms / a.steps
     value = world * n / (ms_per_step * 1e-3) / 1e9
     clocks = clk.summary()
+    clocks["window"] = "timed steps" if (a.kernel_only or a.headline_only) else "timed steps + 0.25 s of the same launches (untimed)"
 
     if a.kernel_only:
         if rank == 0:
