@@ -76,7 +76,7 @@ extern "C" int hsr_set_device(int device)
 extern "C" int hsr_set_option(const char *key, long value)
 {
   if (!key) return -1;
-  if (!strcmp(key, "table")) { if (value < 0 || value > 2) return -1; g_optTable = value; return 0; }
+  if (!strcmp(key, "table")) { if (value < 0 || value > 3) return -1; g_optTable = value; return 0; }
   if (!strcmp(key, "warps")) { if (value < 0 || value > 32) return -1; g_optWarps = value; return 0; }
   if (!strcmp(key, "chunk_mb")) { if (value < 0) return -1; g_optChunkMb = value; return 0; }
   if (!strcmp(key, "index")) { if (value < 0 || value > 2) return -1; g_optIndex = value; return 0; }
@@ -245,11 +245,30 @@ extern "C" int hsr_mt_partition(const hsr_block_t *blocks, size_t count, int par
 
 // ------------------------------------------------------------------------------------------------ kernel launch
 
+static int sm_count()
+{
+  static std::atomic<int> cached{0};
+  int v = cached;
+  if (v == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) {
+      (void)cudaGetLastError();
+      v = 148;
+    }
+    cached = v;
+  }
+  return v;
+}
+
 static int pick_table(int bits, size_t units = (size_t)-1)
 {
   const long opt = g_optTable;
   if (opt == 1) return TK_RANK;
   if (opt == 2) return bits <= 12 ? TK_PACKED : TK_RANK;
+  if (opt == 3) return bits >= 13 ? TK_WIDE : TK_PACKED;
+  // at most one unit per SM (one raw / block_ stream, a few huge mt_ blocks): every unit can have an SM's whole
+  // shared memory, so 13..15 bits also get a one-lookup table (TK_WIDE, 40..160 KB) and only the row latency counts
+  if (bits >= 13 && units <= (size_t)sm_count()) return TK_WIDE;
   // measured on B200 (profiles/r1/sweep_1g_v5.jsonl): the packed slot table wins while it leaves >= 19 CTAs per
   // SM resident (4 / 8 KB at 10 / 11 bits); at 12 bits its 16 KB cost more occupancy than the second lookup costs
   // ... unless there are too few units to fill the GPU anyway (a single raw / block_ stream is ONE warp): then
@@ -268,11 +287,12 @@ static const KernelEntry &kernel_entry(int family, int N, int bits, int table)
 struct LaunchInfo {
   int ctasPerSm = 0, smCount = 0;
 };
+static inline size_t dynamic_smem(const KernelEntry &ke) { return ke.dynamic ? (size_t)ke.smemBytes : 0; }
 
 static std::mutex g_attrMutex;
 
 // residency of a one-warp-CTA kernel, queried once per (kernel, device)
-static bool prepare_kernel(const void *fn, LaunchInfo *li)
+static bool prepare_kernel(const void *fn, LaunchInfo *li, size_t dynamicSmem = 0)
 {
   struct Key { const void *fn; int dev; LaunchInfo li; };
   static std::vector<Key> cache;
@@ -282,8 +302,10 @@ static bool prepare_kernel(const void *fn, LaunchInfo *li)
   for (auto &k : cache)
     if (k.fn == fn && k.dev == dev) { *li = k.li; return true; }
   CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), return false);
+  if (dynamicSmem)
+    CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynamicSmem), return false);
   LaunchInfo out;
-  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out.ctasPerSm, fn, 32, 0), return false);
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out.ctasPerSm, fn, 32, dynamicSmem), return false);
   CU_TRY(cudaDeviceGetAttribute(&out.smCount, cudaDevAttrMultiProcessorCount, dev), return false);
   if (out.ctasPerSm < 1) { set_err("kernel does not fit on an SM"); return false; }
   cache.push_back({fn, dev, out});
@@ -303,12 +325,12 @@ static int launch_units(int family, int N, int bits, const uint8_t *dIn, uint64_
   void *args[] = {&p};
   CU_TRY(cudaMemsetAsync(dCounter, 0, 4, st), return -1); // work counter only; status bits accumulate
   LaunchInfo li;
-  if (!prepare_kernel(ke.units, &li)) return -1;
+  if (!prepare_kernel(ke.units, &li, dynamic_smem(ke))) return -1;
   // persistent one-warp CTAs: every SM filled to its residency limit, units handed out by an atomic counter
   const long optWarps = g_optWarps;
   const uint32_t perSm = optWarps > 0 ? std::min<uint32_t>((uint32_t)optWarps, (uint32_t)li.ctasPerSm) : (uint32_t)li.ctasPerSm;
   const uint32_t grid = std::min<uint32_t>(numBlocks, perSm * (uint32_t)li.smCount);
-  CU_TRY(cudaLaunchKernel(ke.units, dim3(grid), dim3(32), args, 0, st), return -1);
+  CU_TRY(cudaLaunchKernel(ke.units, dim3(grid), dim3(32), args, dynamic_smem(ke), st), return -1);
   return 1;
 }
 
@@ -319,7 +341,9 @@ static int launch_block_stream(int N, int bits, const uint8_t *dIn, uint64_t inL
   const KernelEntry &ke = kernel_entry(HSR_BLOCK, N, bits, table);
   BlockStreamParams p{dIn, dOut, nullptr, BlockStreamDesc{0, inLength, 0, n}, 1u, dCounter, nullptr};
   void *args[] = {&p};
-  CU_TRY(cudaLaunchKernel(ke.block, dim3(1), dim3(32), args, 0, st), return -1);
+  LaunchInfo li;
+  if (!prepare_kernel(ke.block, &li, dynamic_smem(ke))) return -1;
+  CU_TRY(cudaLaunchKernel(ke.block, dim3(1), dim3(32), args, dynamic_smem(ke), st), return -1);
   return 1;
 }
 
@@ -334,9 +358,9 @@ static int launch_block_batch(int N, int bits, const uint8_t *dIn, uint8_t *dOut
   void *args[] = {&p};
   CU_TRY(cudaMemsetAsync(dCounter, 0, 4, st), return -1);
   LaunchInfo li;
-  if (!prepare_kernel(ke.block, &li)) return -1;
+  if (!prepare_kernel(ke.block, &li, dynamic_smem(ke))) return -1;
   const uint32_t grid = std::min<uint32_t>(count, (uint32_t)(li.ctasPerSm * li.smCount));
-  CU_TRY(cudaLaunchKernel(ke.block, dim3(grid), dim3(32), args, 0, st), return -1);
+  CU_TRY(cudaLaunchKernel(ke.block, dim3(grid), dim3(32), args, dynamic_smem(ke), st), return -1);
   return 1;
 }
 

@@ -19,6 +19,10 @@
 //             and O(256 + 2^b/16) to build instead of O(2^b).
 //   TK_PACKED one u32 per slot {freq : 12 | symbol : 8 | slot - cumul : 12}, bits <= 12, one lookup on the chain
 //             (the reference's hist_dec_pack_t idea, src/hist.h:46-50, with the bias pre-subtracted).
+//   TK_WIDE   bits >= 13, for launches with at most one unit per SM (a single raw / block_ stream, a handful of huge
+//             mt_ blocks): one u32 per slot {freq : 16 | slot - cumul : 16} plus one u8 per slot (symbol) — two
+//             INDEPENDENT lookups, one on the chain (the reference's hist_dec3_t idea, src/hist.h:39-44). 5 * 2^b
+//             bytes = 160 KB at 15 bits: dynamic shared memory, one CTA per SM, which is all such a launch can use.
 // Compressed words are staged by cp.async (LDGSTS, 16 B per lane) into a ring of overlapping linear segments, so
 // the data-dependent word reads are LDS, never exposed DRAM latency.
 #pragma once
@@ -59,7 +63,7 @@ constexpr uint32_t kConsumePoint16 = 1u << 15; // src/rans.h:8
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kRowUnroll = HSR_ROW_UNROLL;
 
-enum TableKind : int { TK_RANK = 1, TK_PACKED = 2 };
+enum TableKind : int { TK_RANK = 1, TK_PACKED = 2, TK_WIDE = 3 };
 
 // ---------------------------------------------------------------------------------------------- small helpers
 
@@ -90,6 +94,12 @@ __device__ __forceinline__ uint32_t declare_smem()
   uint32_t base;
   asm volatile(".shared .align 16 .b8 hsr_smem_arr[%1];\n\tmov.u32 %0, hsr_smem_arr;" : "=r"(base) : "n"(BYTES));
   return base;
+}
+// kernels whose tables exceed the 48 KB static limit take the whole CTA allocation as dynamic shared memory
+__device__ __forceinline__ uint32_t dynamic_smem_base()
+{
+  extern __shared__ __align__(16) uint8_t hsr_dynamic_smem[];
+  return (uint32_t)__cvta_generic_to_shared(hsr_dynamic_smem);
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -134,7 +144,8 @@ template <int BITS, int N, int TK>
 struct WarpLayout {
   static_assert(BITS >= 10 && BITS <= 15, "probability bits 10..15");
   static_assert(N == 32 || N == 64, "32 or 64 interleaved states");
-  static_assert(TK == TK_RANK || (TK == TK_PACKED && BITS <= 12), "packed slot table only up to 12 bits");
+  static_assert(TK == TK_RANK || (TK == TK_PACKED && BITS <= 12) || (TK == TK_WIDE && BITS >= 13),
+                "packed slot table up to 12 bits, wide slot tables from 13 bits");
 
   static constexpr int kSlots = 1 << BITS;
   static constexpr int kGroups = kSlots / 16;       // bitmap-rank groups of 16 slots
@@ -142,6 +153,8 @@ struct WarpLayout {
   static constexpr int kEntBytes = 256 * 4;
   static constexpr int kSymBytes = 256;
   static constexpr int kPackedBytes = TK == TK_PACKED ? kSlots * 4 : 0;
+  static constexpr int kWideBytes = TK == TK_WIDE ? kSlots * 5 : 0; // u32 {freq, bias} per slot, then u8 symbol per slot
+  static constexpr bool kDynamic = TK == TK_WIDE;
 
   // word ring: kBufs linear segments of kSeg bytes; consecutive segments overlap by one worst-case row
   static constexpr int kSeg = 512;                  // one 16-byte cp.async per lane
@@ -154,12 +167,14 @@ struct WarpLayout {
   static constexpr int kOffEnt = kOffGrp + kGrpBytes;
   static constexpr int kOffSym = kOffEnt + kEntBytes;
   static constexpr int kOffPacked = kOffSym + kSymBytes;
-  static constexpr int kOffRing = kOffPacked + kPackedBytes;
+  static constexpr int kOffWide = kOffPacked + kPackedBytes;
+  static constexpr int kOffWideSym = kOffWide + (TK == TK_WIDE ? kSlots * 4 : 0);
+  static constexpr int kOffRing = kOffWide + kWideBytes;
   static constexpr int kOffBar = kOffRing + kRingBytes;   // one mbarrier per ring buffer (TMA bulk copies)
   static constexpr int kOffTile = kOffBar + 32;           // output staging tile (HSR_OUT_TILE experiments)
   static constexpr int kTileBytes = HSR_OUT_TILE ? 512 : 0;
   static constexpr int kBytes = kOffTile + kTileBytes;    // per warp (= per CTA), multiple of 16
-  static_assert(kBytes % 16 == 0 && kBytes <= 48 * 1024, "static shared memory budget");
+  static_assert(kBytes % 16 == 0 && kBytes <= (kDynamic ? 227 : 48) * 1024, "shared memory budget");
 };
 
 // ---------------------------------------------------------------------------------------------- word ring
@@ -546,6 +561,20 @@ __device__ __forceinline__ TableInfo build_tables(uint32_t smemWarp, const uint8
     }
     __syncwarp();
   }
+  if constexpr (TK == TK_WIDE) {
+    // expand to {freq:16 | slot - cumul:16} and the symbol per slot
+    const uint32_t sW = smemWarp + L::kOffWide, sWs = smemWarp + L::kOffWideSym;
+    for (uint32_t slot = lane; slot < (uint32_t)L::kSlots; slot += 32u) {
+      const uint32_t g = lds_u32(sGrp + ((slot >> 4) << 2));
+      const uint32_t rank = (g >> 16) + __popc(g << (31u - (slot & 15u)));
+      const uint32_t e = lds_u32(sEnt + rank * 4u);
+      const uint32_t f = (uint32_t)L::kSlots + (uint32_t)(int32_t)(int16_t)(e & 0xffffu);
+      const uint32_t bias = (slot + (uint32_t)((int32_t)e >> 16)) & 0xffffu;
+      sts_u32(sW + slot * 4u, (f << 16) | bias);
+      sts_u8(sWs + slot, lds_u8(sSym + rank));
+    }
+    __syncwarp();
+  }
   return info;
 }
 
@@ -555,7 +584,7 @@ template <int BITS, int N, int TK>
 struct Decoder {
   using L = WarpLayout<BITS, N, TK>;
 
-  uint32_t sGrp, sEnt, sSym, sPk, sTile; // shared addresses, compile-time constants after inlining
+  uint32_t sGrp, sEnt, sSym, sPk, sW, sWs, sTile; // shared addresses, compile-time constants after inlining
 
   __device__ __forceinline__ void init(uint32_t smemWarp)
   {
@@ -564,6 +593,8 @@ struct Decoder {
     sEnt = smemWarp + L::kOffEnt;
     sSym = smemWarp + L::kOffSym;
     sPk = smemWarp + L::kOffPacked;
+    sW = smemWarp + L::kOffWide;
+    sWs = smemWarp + L::kOffWideSym;
   }
 
   // symbol lookup + state update for one state; returns the symbol (low byte significant)
@@ -588,6 +619,27 @@ struct Decoder {
     const uint32_t e = lds_u32(sPk + ((x & (uint32_t)(L::kSlots - 1)) << 2));
     x = (x >> BITS) * (e >> 20) + (e & 0xfffu);
     return e >> 12;
+  }
+
+  __device__ __forceinline__ uint32_t symbol_step_wide(uint32_t &x) const
+  {
+    const uint32_t slot = x & (uint32_t)(L::kSlots - 1);
+    const uint32_t e = lds_u32(sW + (slot << 2));
+    const uint32_t s = lds_u8(sWs + slot); // off the chain
+    x = (x >> BITS) * (e >> 16) + (e & 0xffffu);
+    return s;
+  }
+
+  // kMode 0: packed table, 1: rank table with all symbols present, 2: rank table with the rank->symbol map, 3: wide
+  template <int kMode>
+  __device__ __forceinline__ uint32_t symbol_step(uint32_t &x) const
+  {
+    if constexpr (kMode == 0)
+      return symbol_step_packed(x);
+    else if constexpr (kMode == 3)
+      return symbol_step_wide(x);
+    else
+      return symbol_step_rank<kMode == 1>(x);
   }
 
   // Renormalise one full half-row; `wp` is the shared address of the warp cursor in the word ring. Written in
@@ -712,15 +764,9 @@ struct Decoder {
     for (; r < rows; r++) {
       ring.advance_if_needed(lane);
       uint32_t s0, s1 = 0;
-      if constexpr (kMode == 0) {
-        s0 = symbol_step_packed(x0);
-        if constexpr (N == 64)
-          s1 = symbol_step_packed(x1);
-      } else {
-        s0 = symbol_step_rank<kMode == 1>(x0);
-        if constexpr (N == 64)
-          s1 = symbol_step_rank<kMode == 1>(x1);
-      }
+      s0 = symbol_step<kMode>(x0);
+      if constexpr (N == 64)
+        s1 = symbol_step<kMode>(x1);
       st_global_u8(outLane, s0);
       renorm(x0, ring.wp, ltMask);
       if constexpr (N == 64) {
@@ -736,7 +782,9 @@ struct Decoder {
   {
     while (nrows) { // 64-bit row counts are split so the hot loop keeps a 32-bit counter
       const uint32_t chunk = nrows > 0x40000000ull ? 0x40000000u : (uint32_t)nrows;
-      if (TK == TK_PACKED && !info.degenerate)
+      if (TK == TK_WIDE)
+        rows_impl<3>(x0, x1, ring, outLane, chunk, lane, ltMask);
+      else if (TK == TK_PACKED && !info.degenerate)
         rows_impl<0>(x0, x1, ring, outLane, chunk, lane, ltMask);
       else if (info.allPresent)
         rows_impl<1>(x0, x1, ring, outLane, chunk, lane, ltMask);

@@ -51,7 +51,11 @@ template <int BITS, int N, int TK>
 __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
 {
   using L = WarpLayout<BITS, N, TK>;
-  const uint32_t sw = declare_smem<L::kBytes>();
+  uint32_t sw;
+  if constexpr (L::kDynamic)
+    sw = dynamic_smem_base();
+  else
+    sw = declare_smem<L::kBytes>();
   const uint32_t lane = lane_id();
   const uint32_t ltMask = lanemask_lt();
   const uint32_t lanePos = idx2idx_lane(lane);
@@ -247,7 +251,11 @@ template <int BITS, int N, int TK>
 __device__ __forceinline__ void block_kernel_body(const BlockStreamParams &p)
 {
   using L = WarpLayout<BITS, N, TK>;
-  const uint32_t sw = declare_smem<L::kBytes>();
+  uint32_t sw;
+  if constexpr (L::kDynamic)
+    sw = dynamic_smem_base();
+  else
+    sw = declare_smem<L::kBytes>();
   const uint32_t lane = lane_id();
   const uint32_t ltMask = lanemask_lt();
   const uint32_t lanePos = idx2idx_lane(lane);
@@ -283,12 +291,13 @@ typedef void (*block_kernel_t)(BlockStreamParams);
 struct KernelEntry {
   const void *units; // mt_ blocks / fills / one raw stream; one warp per CTA, persistent
   const void *block; // block_ framing, one warp
-  int smemBytes;     // static shared memory per CTA
+  int smemBytes;     // shared memory per CTA
+  int dynamic;       // 1: smemBytes is DYNAMIC shared memory (tables beyond the 48 KB static limit), passed at launch
 };
 
 // defined in hsr_kernels_n32.cu / hsr_kernels_n64.cu; index [bits - 10][table - 1]
-extern const KernelEntry kKernels32[6][2];
-extern const KernelEntry kKernels64[6][2];
+extern const KernelEntry kKernels32[6][3];
+extern const KernelEntry kKernels64[6][3];
 // defined in hsr_kernels_aux.cu; index [bits - 10] (bitmap-rank table only, units kernel only)
 extern const KernelEntry kKernelsRaw16[6]; // rANS32x16_16w
 extern const KernelEntry kKernelsBlk32[6]; // rANS32x32_32blk_16w

@@ -218,7 +218,7 @@ __device__ __forceinline__ void blk32_kernel_body(const DecodeParams &p)
 
 HSR_AUX_DEFINE(10) HSR_AUX_DEFINE(11) HSR_AUX_DEFINE(12) HSR_AUX_DEFINE(13) HSR_AUX_DEFINE(14) HSR_AUX_DEFINE(15)
 
-#define HSR_AUX_ENTRY(name, BITS) { (const void *)name##BITS, nullptr, WarpLayout<BITS, 32, TK_RANK>::kBytes }
+#define HSR_AUX_ENTRY(name, BITS) { (const void *)name##BITS, nullptr, WarpLayout<BITS, 32, TK_RANK>::kBytes, 0 }
 
 extern const KernelEntry kKernelsRaw16[6] = { HSR_AUX_ENTRY(raw16_b, 10), HSR_AUX_ENTRY(raw16_b, 11), HSR_AUX_ENTRY(raw16_b, 12),
                                               HSR_AUX_ENTRY(raw16_b, 13), HSR_AUX_ENTRY(raw16_b, 14), HSR_AUX_ENTRY(raw16_b, 15) };

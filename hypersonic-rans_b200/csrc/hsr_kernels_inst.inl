@@ -20,15 +20,17 @@ namespace hsr {
   { block_kernel_body<BITS, HSR_N, TK>(p); }
 
 #define HSR_ENTRY(BITS, TK)                                                                                           \
-  { (const void *)HSR_NAME(units_n, BITS, TK), (const void *)HSR_NAME(block_n, BITS, TK), WarpLayout<BITS, HSR_N, TK>::kBytes }
-#define HSR_NONE { nullptr, nullptr, 0 }
+  { (const void *)HSR_NAME(units_n, BITS, TK), (const void *)HSR_NAME(block_n, BITS, TK), WarpLayout<BITS, HSR_N, TK>::kBytes,         \
+    WarpLayout<BITS, HSR_N, TK>::kDynamic ? 1 : 0 }
+#define HSR_NONE { nullptr, nullptr, 0, 0 }
 
 HSR_DEFINE(10, 1) HSR_DEFINE(11, 1) HSR_DEFINE(12, 1) HSR_DEFINE(13, 1) HSR_DEFINE(14, 1) HSR_DEFINE(15, 1)
 HSR_DEFINE(10, 2) HSR_DEFINE(11, 2) HSR_DEFINE(12, 2)
+HSR_DEFINE(13, 3) HSR_DEFINE(14, 3) HSR_DEFINE(15, 3)
 
-extern const KernelEntry HSR_CAT(kKernels, HSR_N)[6][2] = {
-  { HSR_ENTRY(10, 1), HSR_ENTRY(10, 2) }, { HSR_ENTRY(11, 1), HSR_ENTRY(11, 2) }, { HSR_ENTRY(12, 1), HSR_ENTRY(12, 2) },
-  { HSR_ENTRY(13, 1), HSR_NONE }, { HSR_ENTRY(14, 1), HSR_NONE }, { HSR_ENTRY(15, 1), HSR_NONE },
+extern const KernelEntry HSR_CAT(kKernels, HSR_N)[6][3] = {
+  { HSR_ENTRY(10, 1), HSR_ENTRY(10, 2), HSR_NONE }, { HSR_ENTRY(11, 1), HSR_ENTRY(11, 2), HSR_NONE }, { HSR_ENTRY(12, 1), HSR_ENTRY(12, 2), HSR_NONE },
+  { HSR_ENTRY(13, 1), HSR_NONE, HSR_ENTRY(13, 3) }, { HSR_ENTRY(14, 1), HSR_NONE, HSR_ENTRY(14, 3) }, { HSR_ENTRY(15, 1), HSR_NONE, HSR_ENTRY(15, 3) },
 };
 
 } // namespace hsr

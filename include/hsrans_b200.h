@@ -43,7 +43,8 @@ int hsr_device_count(void);
 /* Thread-local description of the last failure in this thread ("" if none). */
 const char *hsr_last_error(void);
 /* Tuning knobs, for benchmarking variants without rebuilding. Unknown keys return -1.
- *   "table"      0 = auto (packed slot table for bits <= 12, bitmap-rank table above), 1 = bitmap-rank, 2 = packed
+ *   "table"      0 = auto (packed slot table for bits <= 12, bitmap-rank table above; wide one-lookup tables for
+ *                13..15 bits when a launch has at most one unit per SM), 1 = bitmap-rank, 2 = packed, 3 = wide
  *   "warps"      cap on resident one-warp CTAs per SM for the mt_ kernel (1..32, 0 = as many as fit; experiments)
  *   "chunk_mb"   host pipeline chunk size in MiB for hsr_decode on mt_ streams (0 = auto)
  *   "index"      block index of device-resident mt_ streams: 0 = segment-parallel with serial fallback,

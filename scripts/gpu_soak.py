@@ -51,7 +51,7 @@ for case in range(a.cases):
             if len(set(data.tolist()[:64])) == 1 and np.all(data == data[0]):
                 continue
             fails.append((case, fam, states, bits, n, pname, f"encode: {exc}")); continue
-        table = int(rng.integers(0, 3))
+        table = int(rng.integers(0, 4))
         pkg.set_option("table", table)
         got_n, got = pkg.decode(fam, states, bits, stream, n)
         pkg.set_option("table", 0)

@@ -13,7 +13,7 @@ for key in sorted(z.files):
     if name not in ("multi", "runs", "tiny65", "small") or int(bits) not in (10, 12, 15):
         continue
     data = z[f"in/{name}"]
-    for table in (0, 1):
+    for table in (0, 1, 3):
         pkg.set_option("table", table)
         n, out = pkg.decode(int(fam), int(states), int(bits), z[key], data.size)
         ok = n == data.size and np.array_equal(out[:n], data)

@@ -27,7 +27,7 @@ def _check(gpu, fam, states, bits, stream, data, label=""):
     assert out[n:].size == 0 or np.all(out[n:] == 0xCC)  # never writes past the decoded length
 
 
-@pytest.mark.parametrize("table", [0, 1])
+@pytest.mark.parametrize("table", [0, 1, 3])
 def test_golden_streams_bit_exact(gpu, golden, table):
     gpu.set_option("table", table)
     try:
