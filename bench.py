@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-only", action="store_true", help="skip e2e / index / CPU legs (profiling runs)")
-    ap.add_argument("--table", type=int, default=0, help="hsr_set_option table: 0 auto, 1 bitmap-rank, 2 packed")
+    ap.add_argument("--table", type=int, default=0, help="hsr_set_option table: 0 auto, 1 bitmap-rank, 2 packed, 3 wide (bits >= 13)")
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="cap resident one-warp CTAs per SM (occupancy experiments)")
     ap.add_argument("--headline-only", action="store_true", help="skip the configs 1-3 leg (profiling runs: only the headline kernel launches)")
     ap.add_argument("--extra", action="store_true", help="also measure batch decode, the device encoder and the histogram kernels")
