@@ -261,9 +261,9 @@ def test_full_size_100mb_round_trip(gpu):
     """BASELINE.json sizes: 100,000,000-byte Zipf stream; decode(encode(x)) == x for configs 1-3 and the mt_ codec."""
     n = 100_000_000
     data = _zipf(gpu, n, 1.0, 42, 65536)
-    cases = [(ck.RAW, 64, 12)]
+    cases = [(ck.RAW, 64, 12), (ck.RAW, 64, 15)]  # 15 bits, one unit: the wide one-lookup table (160 KB of shared memory)
     if ck.have_ref():
-        cases += [(ck.MT, 64, 15), (ck.BLOCK, 32, 10), (ck.RAW, 32, 11)]
+        cases += [(ck.MT, 64, 15), (ck.BLOCK, 32, 10), (ck.RAW, 32, 11), (ck.BLOCK, 64, 14)]
     for fam, states, bits in cases:
         stream = ck.encode(fam, states, bits, data)
         n_out, out = gpu.decode(fam, states, bits, stream, n)
