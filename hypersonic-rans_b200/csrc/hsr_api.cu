@@ -260,7 +260,8 @@ static int sm_count()
   return v;
 }
 
-static int pick_table(int bits, size_t units = (size_t)-1)
+// `decodedBytes` = bytes the launch decodes in total (0 = unknown): the wide tables cost ~40 us to build per unit
+static int pick_table(int bits, size_t units = (size_t)-1, uint64_t decodedBytes = 0)
 {
   const long opt = g_optTable;
   if (opt == 1) return TK_RANK;
@@ -268,7 +269,8 @@ static int pick_table(int bits, size_t units = (size_t)-1)
   if (opt == 3) return bits >= 13 ? TK_WIDE : TK_PACKED;
   // at most one unit per SM (one raw / block_ stream, a few huge mt_ blocks): every unit can have an SM's whole
   // shared memory, so 13..15 bits also get a one-lookup table (TK_WIDE, 40..160 KB) and only the row latency counts
-  if (bits >= 13 && units <= (size_t)sm_count()) return TK_WIDE;
+  // ... provided the units are long enough to pay for filling 2^bits slots (break-even near 100 KB per unit)
+  if (bits >= 13 && units <= (size_t)sm_count() && decodedBytes / (units ? units : 1) >= (256u << 10)) return TK_WIDE;
   // measured on B200 (profiles/r1/sweep_1g_v5.jsonl): the packed slot table wins while it leaves >= 19 CTAs per
   // SM resident (4 / 8 KB at 10 / 11 bits); at 12 bits its 16 KB cost more occupancy than the second lookup costs
   // ... unless there are too few units to fill the GPU anyway (a single raw / block_ stream is ONE warp): then
@@ -316,10 +318,10 @@ static bool prepare_kernel(const void *fn, LaunchInfo *li, size_t dynamicSmem = 
 // launches the units kernel over `numBlocks` records of a device-resident index
 static int launch_units(int family, int N, int bits, const uint8_t *dIn, uint64_t inBase, uint8_t *dOut, uint64_t outBase,
                         const hsr_block_t *dBlocks, uint32_t numBlocks, uint32_t *dCounter, cudaStream_t st,
-                        uint32_t *dStreamStatus = nullptr)
+                        uint32_t *dStreamStatus = nullptr, uint64_t decodedBytes = 0)
 {
   if (numBlocks == 0) return 0;
-  const int table = pick_table(bits, numBlocks);
+  const int table = pick_table(bits, numBlocks, decodedBytes);
   const KernelEntry &ke = kernel_entry(family, N, bits, table);
   DecodeParams p{dIn, inBase, dOut, outBase, dBlocks, numBlocks, dCounter, dStreamStatus};
   void *args[] = {&p};
@@ -337,7 +339,7 @@ static int launch_units(int family, int N, int bits, const uint8_t *dIn, uint64_
 static int launch_block_stream(int N, int bits, const uint8_t *dIn, uint64_t inLength, uint8_t *dOut, uint64_t n,
                                uint32_t *dCounter, cudaStream_t st)
 {
-  const int table = pick_table(bits, 1);
+  const int table = pick_table(bits, 1, n);
   const KernelEntry &ke = kernel_entry(HSR_BLOCK, N, bits, table);
   BlockStreamParams p{dIn, dOut, nullptr, BlockStreamDesc{0, inLength, 0, n}, 1u, dCounter, nullptr};
   void *args[] = {&p};
@@ -349,10 +351,10 @@ static int launch_block_stream(int N, int bits, const uint8_t *dIn, uint64_t inL
 
 // many independent block_ streams, one warp each
 static int launch_block_batch(int N, int bits, const uint8_t *dIn, uint8_t *dOut, const BlockStreamDesc *dStreams, uint32_t count,
-                              uint32_t *dCounter, uint32_t *dStreamStatus, cudaStream_t st)
+                              uint32_t *dCounter, uint32_t *dStreamStatus, cudaStream_t st, uint64_t decodedBytes = 0)
 {
   if (count == 0) return 0;
-  const int table = pick_table(bits, count);
+  const int table = pick_table(bits, count, decodedBytes);
   const KernelEntry &ke = kernel_entry(HSR_BLOCK, N, bits, table);
   BlockStreamParams p{dIn, dOut, dStreams, BlockStreamDesc{0, 0, 0, 0}, count, dCounter, dStreamStatus};
   void *args[] = {&p};
@@ -444,6 +446,7 @@ struct hsr_stream {
   hsr_block_t *dBlocks = nullptr;
   uint32_t *dCounter = nullptr;    // [0] work counter, [1] status
   uint64_t outOffset = 0, outBytes = 0;
+  uint64_t decodedTotal = 0; // bytes one decode_async produces (table choice)
   double indexMs = 0;
   // batch of independent streams (hsr_stream_upload_batch): block_ descriptors + per-stream status
   BlockStreamDesc *dDescs = nullptr;
@@ -469,6 +472,12 @@ extern "C" void hsr_stream_free(hsr_stream_t *s) { stream_release(s); }
 
 static bool stream_finish(hsr_stream *s) // uploads the index, allocates the counters
 {
+  s->decodedTotal = s->batch ? s->outBytes : (s->outBytes ? s->outBytes : s->n);
+  if (!s->blocks.empty()) {
+    uint64_t sum = 0;
+    for (const auto &b : s->blocks) sum += b.count;
+    s->decodedTotal = sum;
+  }
   CU_TRY(cudaMalloc(&s->dCounter, 16), return false);
   CU_TRY(cudaMemset(s->dCounter, 0, 16), return false);
   if (!s->blocks.empty()) {
@@ -727,10 +736,11 @@ extern "C" int hsr_stream_decode_async(hsr_stream_t *s, void *dOutV, size_t outC
   if (outCapacity < need) { set_err("outCapacity %zu < %llu", outCapacity, (unsigned long long)need); return -1; }
   const uint64_t outBase = local ? s->outOffset : 0;
   if (s->family == HSR_BLOCK && s->batch)
-    return launch_block_batch(s->N, s->bits, s->dIn, dOut, s->dDescs, s->numDescs, s->dCounter, nullptr, st);
+    return launch_block_batch(s->N, s->bits, s->dIn, dOut, s->dDescs, s->numDescs, s->dCounter, nullptr, st, s->decodedTotal);
   if (s->family == HSR_BLOCK)
     return launch_block_stream(s->N, s->bits, s->dIn, s->compLen, dOut, s->n, s->dCounter, st);
-  return launch_units(s->family, s->N, s->bits, s->dIn, s->inBase, dOut, outBase, s->dBlocks, (uint32_t)s->blocks.size(), s->dCounter, st);
+  return launch_units(s->family, s->N, s->bits, s->dIn, s->inBase, dOut, outBase, s->dBlocks, (uint32_t)s->blocks.size(), s->dCounter, st,
+                      nullptr, s->decodedTotal);
 }
 
 extern "C" unsigned hsr_stream_status(hsr_stream_t *s)
@@ -884,7 +894,10 @@ static bool run_units_pipelined(DeviceCtx *c, int family, int N, int bits, uint8
     const uint64_t needEnd = units[b - 1].inEnd;
     while (piece + 1 < fl.ends.size() && fl.ends[piece] < needEnd) piece++;
     CU_TRY(cudaStreamWaitEvent(c->sRun, c->evIn[piece], 0), return false);
-    if (launch_units(family, N, bits, c->dIn, fl.lo, c->dOut, outLo, devBlocks + (a - first), (uint32_t)(b - a), c->dCounters + 4 * r, c->sRun) < 0)
+    uint64_t rangeDecoded = 0;
+    for (size_t k = a; k < b; k++) rangeDecoded += units[k].count;
+    if (launch_units(family, N, bits, c->dIn, fl.lo, c->dOut, outLo, devBlocks + (a - first), (uint32_t)(b - a), c->dCounters + 4 * r, c->sRun,
+                     nullptr, rangeDecoded) < 0)
       return false;
     CU_TRY(cudaEventRecord(c->evRun[r], c->sRun), return false);
     CU_TRY(cudaStreamWaitEvent(c->sOut, c->evRun[r], 0), return false);
@@ -1010,14 +1023,19 @@ extern "C" size_t hsr_decode_batch(int family, int N, int bits, const uint8_t *i
     if (!grow(c->dBlocks, c->blocksCap, bytes / sizeof(hsr_block_t) + 1)) return 0;
     CU_TRY(cudaMemcpyAsync(c->dBlocks, descs.data(), bytes, cudaMemcpyHostToDevice, c->sRun), return 0);
     // per-stream status is indexed by the position in `descs`; map back below
+    uint64_t batchDecoded = 0;
+    for (const auto &d : descs) batchDecoded += d.n;
     if (launch_block_batch(N, bits, c->dIn, c->dOut, reinterpret_cast<const BlockStreamDesc *>(c->dBlocks), (uint32_t)descs.size(),
-                           c->dCounters, dStreamStatus, c->sRun) < 0)
+                           c->dCounters, dStreamStatus, c->sRun, batchDecoded) < 0)
       return 0;
   } else {
     if (!grow(c->dBlocks, c->blocksCap, units.size())) return 0;
     std::stable_sort(units.begin(), units.end(), [](const hsr_block_t &a, const hsr_block_t &b) { return a.count > b.count; }); // longest first
     CU_TRY(cudaMemcpyAsync(c->dBlocks, units.data(), units.size() * sizeof(hsr_block_t), cudaMemcpyHostToDevice, c->sRun), return 0);
-    if (launch_units(family, N, bits, c->dIn, inLo, c->dOut, outLo, c->dBlocks, (uint32_t)units.size(), c->dCounters, c->sRun, dStreamStatus) < 0)
+    uint64_t batchDecoded = 0;
+    for (const auto &u : units) batchDecoded += u.count;
+    if (launch_units(family, N, bits, c->dIn, inLo, c->dOut, outLo, c->dBlocks, (uint32_t)units.size(), c->dCounters, c->sRun, dStreamStatus,
+                     batchDecoded) < 0)
       return 0;
   }
   std::vector<uint32_t> status(4 + count);
