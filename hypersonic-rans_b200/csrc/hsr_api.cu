@@ -281,8 +281,8 @@ static int pick_table(int bits, size_t units = (size_t)-1, uint64_t decodedBytes
 
 static const KernelEntry &kernel_entry(int family, int N, int bits, int table)
 {
-  if (family == HSR_RAW32BLK) return kKernelsBlk32[bits - 10];
-  if (N == 16) return kKernelsRaw16[bits - 10];
+  if (family == HSR_RAW32BLK) return kKernelsBlk32[bits - 10][table == TK_RANK ? 0 : 1];
+  if (N == 16) return kKernelsRaw16[bits - 10][table == TK_RANK ? 0 : 1];
   return (N == 32 ? kKernels32 : kKernels64)[bits - 10][table - 1];
 }
 

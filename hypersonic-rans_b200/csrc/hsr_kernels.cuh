@@ -298,8 +298,8 @@ struct KernelEntry {
 // defined in hsr_kernels_n32.cu / hsr_kernels_n64.cu; index [bits - 10][table - 1]
 extern const KernelEntry kKernels32[6][3];
 extern const KernelEntry kKernels64[6][3];
-// defined in hsr_kernels_aux.cu; index [bits - 10] (bitmap-rank table only, units kernel only)
-extern const KernelEntry kKernelsRaw16[6]; // rANS32x16_16w
-extern const KernelEntry kKernelsBlk32[6]; // rANS32x32_32blk_16w
+// defined in hsr_kernels_aux.cu; index [bits - 10][0 = bitmap-rank tables, 1 = one-lookup tables] (units kernel only)
+extern const KernelEntry kKernelsRaw16[6][2]; // rANS32x16_16w
+extern const KernelEntry kKernelsBlk32[6][2]; // rANS32x32_32blk_16w
 
 } // namespace hsr

@@ -11,6 +11,8 @@
 //
 // Both are single recurrences (one warp per stream, latency-bound like every raw stream); throughput comes from
 // batches (hsr_decode_batch), which these kernels serve through the same persistent unit loop.
+#include <type_traits>
+
 #include "hsr_kernels.cuh"
 
 namespace hsr {
@@ -46,17 +48,25 @@ __device__ __forceinline__ bool next_unit(const DecodeParams &p, uint32_t lane, 
 
 // ---------------------------------------------------------------------------------------------- rANS32x16_16w
 
-template <int BITS>
+// which symbol step a unit uses: the fast one-lookup table of this kernel, or the rank tables that are always built
+template <int TK>
+__device__ __forceinline__ int step_mode(const TableInfo &info) { return TK == TK_WIDE ? 3 : (TK == TK_PACKED && !info.degenerate) ? 0 : 2; }
+
+template <int BITS, int TK>
 __device__ __forceinline__ void raw16_kernel_body(const DecodeParams &p)
 {
-  using L = WarpLayout<BITS, 32, TK_RANK>; // a row of 16 consumes at most 32 bytes: inside the 32-state ring's overlap
-  const uint32_t sw = declare_smem<L::kBytes>();
+  using L = WarpLayout<BITS, 32, TK>; // a row of 16 consumes at most 32 bytes: inside the 32-state ring's overlap
+  uint32_t sw;
+  if constexpr (L::kDynamic)
+    sw = dynamic_smem_base();
+  else
+    sw = declare_smem<L::kBytes>();
   const uint32_t lane = lane_id();
   const uint32_t ltMask = lanemask_lt();
   const bool live = lane < 16u;
   const uint32_t lanePos = idx2idx16_lane(lane & 15u);
 
-  Decoder<BITS, 32, TK_RANK> dec;
+  Decoder<BITS, 32, TK> dec;
   dec.init(sw);
   Ring<L> ring;
 #if HSR_RING_TMA
@@ -72,7 +82,7 @@ __device__ __forceinline__ void raw16_kernel_body(const DecodeParams &p)
     const uint8_t *countsPtr = u.base; // counts, then u32 states[16], then words (src/rANS32x16_16w.cpp:183-203)
     const uint8_t *statesPtr = u.base + 512;
     const uint8_t *words = u.base + 512 + 4 * 16;
-    const TableInfo info = build_tables<BITS, 32, TK_RANK>(sw, countsPtr, lane);
+    const TableInfo info = build_tables<BITS, 32, TK>(sw, countsPtr, lane);
     if (!info.ok) {
       raise(p.counter, p.streamStatus, u.streamId, HSR_ERR_HIST, lane);
       continue;
@@ -87,17 +97,24 @@ __device__ __forceinline__ void raw16_kernel_body(const DecodeParams &p)
     ring.start_wait();
     const uint64_t rows = (u.count - u.tail) / 16u;
     uint8_t *outLane = u.out + lanePos;
+    auto run = [&](auto modeTag) {
+      constexpr int kMode = decltype(modeTag)::value;
 #pragma unroll 4
-    for (uint64_t r = 0; r < rows; r++) { // :213-238
-      ring.advance_if_needed(lane);
-      const uint32_t s = dec.template symbol_step_rank<false>(x);
-      if (live)
-        st_global_u8(outLane, s);
-      else
-        x = 0x80000000u; // idle lanes: pinned above the consume point, so the unmasked hand-out skips them
-      dec.renorm(x, ring.wp, ltMask);
-      outLane += 16;
-    }
+      for (uint64_t r = 0; r < rows; r++) { // :213-238
+        ring.advance_if_needed(lane);
+        const uint32_t s = dec.template symbol_step<kMode>(x);
+        if (live)
+          st_global_u8(outLane, s);
+        else
+          x = 0x80000000u; // idle lanes: pinned above the consume point, so the unmasked hand-out skips them
+        dec.renorm(x, ring.wp, ltMask);
+        outLane += 16;
+      }
+    };
+    const int mode = step_mode<TK>(info);
+    if (mode == 3) run(std::integral_constant<int, 3>{});
+    else if (mode == 0) run(std::integral_constant<int, 0>{});
+    else run(std::integral_constant<int, 2>{});
     if (u.tail) { // :240-268
       ring.advance_if_needed(lane);
       const bool a = live && lanePos < u.tail;
@@ -117,15 +134,19 @@ __device__ __forceinline__ void raw16_kernel_body(const DecodeParams &p)
 
 // ---------------------------------------------------------------------------------------------- rANS32x32_32blk_16w
 
-template <int BITS>
+template <int BITS, int TK>
 __device__ __forceinline__ void blk32_kernel_body(const DecodeParams &p)
 {
-  using L = WarpLayout<BITS, 32, TK_RANK>;
-  const uint32_t sw = declare_smem<L::kBytes>();
+  using L = WarpLayout<BITS, 32, TK>;
+  uint32_t sw;
+  if constexpr (L::kDynamic)
+    sw = dynamic_smem_base();
+  else
+    sw = declare_smem<L::kBytes>();
   const uint32_t lane = lane_id();
   const uint32_t lanePos = idx2idx_lane(lane); // same permutation as rANS32x32_16w (src/rans32x32_32blk_16w.cpp:235)
 
-  Decoder<BITS, 32, TK_RANK> dec;
+  Decoder<BITS, 32, TK> dec;
   dec.init(sw);
 
   UnitView u;
@@ -138,7 +159,7 @@ __device__ __forceinline__ void blk32_kernel_body(const DecodeParams &p)
     const uint8_t *statesPtr = u.base + 512;
     const uint8_t *sizesPtr = statesPtr + 4 * 32;
     const uint8_t *data = sizesPtr + 4 * 31;
-    const TableInfo info = build_tables<BITS, 32, TK_RANK>(sw, countsPtr, lane);
+    const TableInfo info = build_tables<BITS, 32, TK>(sw, countsPtr, lane);
     if (!info.ok) {
       raise(p.counter, p.streamStatus, u.streamId, HSR_ERR_HIST, lane);
       continue;
@@ -188,13 +209,20 @@ __device__ __forceinline__ void blk32_kernel_body(const DecodeParams &p)
 
     const uint64_t rows = (u.count - u.tail) / 32u;
     uint8_t *outLane = u.out + lanePos;
+    auto run = [&](auto modeTag) {
+      constexpr int kMode = decltype(modeTag)::value;
 #pragma unroll 2
-    for (uint64_t r = 0; r < rows; r++) { // :241-269
-      const uint32_t s = dec.template symbol_step_rank<false>(x);
-      st_global_u8(outLane, s);
-      renorm(true);
-      outLane += 32;
-    }
+      for (uint64_t r = 0; r < rows; r++) { // :241-269
+        const uint32_t s = dec.template symbol_step<kMode>(x);
+        st_global_u8(outLane, s);
+        renorm(true);
+        outLane += 32;
+      }
+    };
+    const int mode = step_mode<TK>(info);
+    if (mode == 3) run(std::integral_constant<int, 3>{});
+    else if (mode == 0) run(std::integral_constant<int, 0>{});
+    else run(std::integral_constant<int, 2>{});
     if (u.tail) { // :271-298
       const bool a = lanePos < u.tail;
       uint32_t t = x;
@@ -212,17 +240,23 @@ __device__ __forceinline__ void blk32_kernel_body(const DecodeParams &p)
 
 // ---------------------------------------------------------------------------------------------- instantiation
 
-#define HSR_AUX_DEFINE(BITS)                                                                                          \
-  __global__ void __launch_bounds__(32, 16) raw16_b##BITS(DecodeParams p) { raw16_kernel_body<BITS>(p); }             \
-  __global__ void __launch_bounds__(32, 16) blk32_b##BITS(DecodeParams p) { blk32_kernel_body<BITS>(p); }
+// per bit width: the bitmap-rank kernel (any number of units) and a one-lookup kernel for launches the host judges
+// latency-bound or small-tabled (packed u32/slot up to 12 bits, wide tables in dynamic shared memory above)
+#define HSR_AUX_DEFINE(BITS, FAST)                                                                                    \
+  __global__ void __launch_bounds__(32, 16) raw16_b##BITS(DecodeParams p) { raw16_kernel_body<BITS, TK_RANK>(p); }    \
+  __global__ void __launch_bounds__(32, 16) blk32_b##BITS(DecodeParams p) { blk32_kernel_body<BITS, TK_RANK>(p); }    \
+  __global__ void __launch_bounds__(32, 16) raw16_fast_b##BITS(DecodeParams p) { raw16_kernel_body<BITS, FAST>(p); }  \
+  __global__ void __launch_bounds__(32, 16) blk32_fast_b##BITS(DecodeParams p) { blk32_kernel_body<BITS, FAST>(p); }
 
-HSR_AUX_DEFINE(10) HSR_AUX_DEFINE(11) HSR_AUX_DEFINE(12) HSR_AUX_DEFINE(13) HSR_AUX_DEFINE(14) HSR_AUX_DEFINE(15)
+HSR_AUX_DEFINE(10, TK_PACKED) HSR_AUX_DEFINE(11, TK_PACKED) HSR_AUX_DEFINE(12, TK_PACKED)
+HSR_AUX_DEFINE(13, TK_WIDE) HSR_AUX_DEFINE(14, TK_WIDE) HSR_AUX_DEFINE(15, TK_WIDE)
 
-#define HSR_AUX_ENTRY(name, BITS) { (const void *)name##BITS, nullptr, WarpLayout<BITS, 32, TK_RANK>::kBytes, 0 }
+#define HSR_AUX_ENTRY(name, BITS, TK) { (const void *)name##BITS, nullptr, WarpLayout<BITS, 32, TK>::kBytes, WarpLayout<BITS, 32, TK>::kDynamic ? 1 : 0 }
+#define HSR_AUX_ROW(prefix, BITS, FAST) { HSR_AUX_ENTRY(prefix##_b, BITS, TK_RANK), HSR_AUX_ENTRY(prefix##_fast_b, BITS, FAST) }
 
-extern const KernelEntry kKernelsRaw16[6] = { HSR_AUX_ENTRY(raw16_b, 10), HSR_AUX_ENTRY(raw16_b, 11), HSR_AUX_ENTRY(raw16_b, 12),
-                                              HSR_AUX_ENTRY(raw16_b, 13), HSR_AUX_ENTRY(raw16_b, 14), HSR_AUX_ENTRY(raw16_b, 15) };
-extern const KernelEntry kKernelsBlk32[6] = { HSR_AUX_ENTRY(blk32_b, 10), HSR_AUX_ENTRY(blk32_b, 11), HSR_AUX_ENTRY(blk32_b, 12),
-                                              HSR_AUX_ENTRY(blk32_b, 13), HSR_AUX_ENTRY(blk32_b, 14), HSR_AUX_ENTRY(blk32_b, 15) };
+extern const KernelEntry kKernelsRaw16[6][2] = { HSR_AUX_ROW(raw16, 10, TK_PACKED), HSR_AUX_ROW(raw16, 11, TK_PACKED), HSR_AUX_ROW(raw16, 12, TK_PACKED),
+                                                 HSR_AUX_ROW(raw16, 13, TK_WIDE), HSR_AUX_ROW(raw16, 14, TK_WIDE), HSR_AUX_ROW(raw16, 15, TK_WIDE) };
+extern const KernelEntry kKernelsBlk32[6][2] = { HSR_AUX_ROW(blk32, 10, TK_PACKED), HSR_AUX_ROW(blk32, 11, TK_PACKED), HSR_AUX_ROW(blk32, 12, TK_PACKED),
+                                                 HSR_AUX_ROW(blk32, 13, TK_WIDE), HSR_AUX_ROW(blk32, 14, TK_WIDE), HSR_AUX_ROW(blk32, 15, TK_WIDE) };
 
 } // namespace hsr
