@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define HSR_VERSION 100
+#define HSR_VERSION 110 /* 110: + HSR_RAW32BLK, stateCount 16, hsr_encode_mt_policy*, table option 3 */
 
 /* Stream framings (SURVEY.md §8a "Stream formats"). */
 typedef enum hsr_family {
