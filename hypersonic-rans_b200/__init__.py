@@ -10,7 +10,7 @@ happens in the hand-written sm_100a kernels under ``csrc/``; there is no Python 
 from .capi import (  # noqa: F401
     HSR_RAW, HSR_BLOCK, HSR_MT, HSR_RAW32BLK, FAMILY_NAMES, HsrError, Block, PreparedStream, lib, lib_path, version, device_count,
     last_error, set_option, get_option, capacity, host_alloc, HostBuffer, decode, decode_batch, decode_mt_multi, mt_index,
-    mt_partition, make_hist, synth_zipf, encode_mt, encode_mt_device, encode_mt_bound, encode_mt_policy, encode_mt_policy_device, observe_hist_device, normalize_hist_device, make_hist_segments_device,
+    mt_partition, make_hist, synth_zipf, encode_mt, encode_mt_device, encode_mt_device_indexed, encode_mt_index_bound, encode_mt_bound, encode_mt_policy, encode_mt_policy_device, observe_hist_device, normalize_hist_device, make_hist_segments_device,
 )
 from .codecs import CODECS, Codec, find_codec  # noqa: F401
 from .sharding import ShardPlan, plan_shards, assemble_on  # noqa: F401

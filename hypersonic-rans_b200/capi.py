@@ -49,6 +49,7 @@ SIGNATURES = {
     "hsr_mt_partition": (C.c_int, [C.POINTER(Block), C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]),
     "hsr_stream_upload": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
     "hsr_stream_from_device": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "hsr_stream_from_device_indexed": (C.c_void_p, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "hsr_stream_upload_batch": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "hsr_stream_free": (None, [C.c_void_p]),
     "hsr_stream_decoded_length": (C.c_uint64, [C.c_void_p]),
@@ -66,6 +67,9 @@ SIGNATURES = {
     "hsr_make_hist_segments_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
     "hsr_encode_mt": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]),
     "hsr_encode_mt_device": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "hsr_encode_mt_device_indexed": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int,
+                                                   C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]),
+    "hsr_encode_mt_index_bound": (C.c_size_t, [C.c_int, C.c_size_t, C.c_size_t]),
     "hsr_encode_mt_bound": (C.c_size_t, [C.c_int, C.c_size_t, C.c_size_t]),
     "hsr_encode_mt_policy": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]),
     "hsr_encode_mt_policy_device": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
@@ -234,6 +238,11 @@ class PreparedStream:
     def from_device(cls, family: int, state_count: int, bits: int, device_ptr: int, length: int) -> "PreparedStream":
         return cls(lib().hsr_stream_from_device(family, state_count, bits, device_ptr, length))
 
+    @classmethod
+    def from_device_indexed(cls, state_count: int, bits: int, device_ptr: int, length: int, d_index: int, num_units: int) -> "PreparedStream":
+        """mt_ stream + the block table its producer wrote (encode_mt_device_indexed): no chain walk."""
+        return cls(lib().hsr_stream_from_device_indexed(state_count, bits, device_ptr, length, d_index, num_units))
+
     decoded_length = property(lambda self: lib().hsr_stream_decoded_length(self.handle))
     shard_out_offset = property(lambda self: lib().hsr_stream_shard_out_offset(self.handle))
     shard_out_bytes = property(lambda self: lib().hsr_stream_shard_out_bytes(self.handle))
@@ -326,6 +335,19 @@ def encode_mt_policy_device(state_count: int, bits: int, d_in: int, length: int,
 def encode_mt_device(state_count: int, bits: int, d_in: int, length: int, d_out: int, out_capacity: int, block_size: int = 0,
                      cuda_stream: int = 0) -> int:
     return lib().hsr_encode_mt_device(state_count, bits, d_in, length, d_out, out_capacity, block_size, cuda_stream)
+
+
+def encode_mt_device_indexed(state_count: int, bits: int, d_in: int, length: int, d_out: int, out_capacity: int, d_index: int,
+                             index_capacity: int, block_size: int = 0, policy: bool = False, cuda_stream: int = 0):
+    """Device encode that also writes the decoder's unit table to d_index. Returns (compressed_bytes, num_units)."""
+    n_units = C.c_size_t(0)
+    comp = lib().hsr_encode_mt_device_indexed(state_count, bits, d_in, length, d_out, out_capacity, block_size, 1 if policy else 0,
+                                              d_index, index_capacity, C.byref(n_units), cuda_stream)
+    return comp, n_units.value
+
+
+def encode_mt_index_bound(state_count: int, length: int, block_size: int = 0) -> int:
+    return lib().hsr_encode_mt_index_bound(state_count, length, block_size)
 
 
 def encode_mt_bound(state_count: int, length: int, block_size: int = 0) -> int:

@@ -14,8 +14,12 @@
 //     cuda_rANS32x16_16w_decode_<b>          replaces rANS32x16_16w_decode_scalar_<b>   (src/rANS32x16_16w.h:9 ...)
 //     cuda_rANS32x32_32blk_16w_decode_<b>    replaces rANS32x32_32blk_16w_decode_scalar_<b> (src/rans32x32_32blk_16w.h:9 ...)
 // for <b> in 10..15, plus the `*_capacity` twins. Same return convention: decoded size, or 0 on any error.
-// The mt_ thread-pool variants take no pool here: the GPU is the pool (hsr_decode_mt_multi spreads one stream
-// over several GPUs the way decode_mt spreads it over threads, src/mt_rANS32x64_16w_decode.cpp:137-265).
+// The mt_ thread-pool entry points have twins with the pool signature as well,
+//     cuda_mt_rANS32xNN_16w_decode_mt_<b>(pInData, inLength, pOutData, outCapacity, thread_pool *)
+// (src/mt_rANS32x64_16w.h:23-28), so that `decode_with_thread_pool_wrapper<>` (src/main.cpp:163-170) instantiates on
+// them and the "decode (multi threaded)" row can be SWAPPED, not only appended to. The pool argument is ignored: the
+// GPU is the pool (hsr_decode_mt_multi spreads one stream over several GPUs the way decode_mt spreads it over
+// threads, src/mt_rANS32x64_16w_decode.cpp:137-265).
 #ifndef HSRANS_B200_CODECS_HPP
 #define HSRANS_B200_CODECS_HPP
 
@@ -46,6 +50,22 @@ HSR_B200_DECODERS(cuda_mt_rANS32x32_16w_decode, HSR_MT, 32)
 HSR_B200_DECODERS(cuda_mt_rANS32x64_16w_decode, HSR_MT, 64)
 HSR_B200_DECODERS(cuda_rANS32x16_16w_decode, HSR_RAW, 16)
 HSR_B200_DECODERS(cuda_rANS32x32_32blk_16w_decode, HSR_RAW32BLK, 32)
+
+struct thread_pool; // src/thread_pool.h:7 (opaque here as there)
+
+#define HSR_B200_POOL_DECODER(name, states, bits)                                                                        \
+  inline size_t name##_##bits(const uint8_t *pInData, const size_t inLength, uint8_t *pOutData, const size_t outCapacity, \
+                              thread_pool * /* the GPU is the pool */)                                                   \
+  {                                                                                                                      \
+    return hsr_decode(HSR_MT, states, bits, pInData, inLength, pOutData, outCapacity);                                   \
+  }
+#define HSR_B200_POOL_DECODERS(name, states)                                                                             \
+  HSR_B200_POOL_DECODER(name, states, 15) HSR_B200_POOL_DECODER(name, states, 14) HSR_B200_POOL_DECODER(name, states, 13) \
+  HSR_B200_POOL_DECODER(name, states, 12) HSR_B200_POOL_DECODER(name, states, 11) HSR_B200_POOL_DECODER(name, states, 10)
+HSR_B200_POOL_DECODERS(cuda_mt_rANS32x32_16w_decode_mt, 32)
+HSR_B200_POOL_DECODERS(cuda_mt_rANS32x64_16w_decode_mt, 64)
+#undef HSR_B200_POOL_DECODERS
+#undef HSR_B200_POOL_DECODER
 
 #undef HSR_B200_DECODERS
 #undef HSR_B200_DECODER

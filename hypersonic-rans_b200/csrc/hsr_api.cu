@@ -9,11 +9,15 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -48,7 +52,21 @@ static void set_err(const char *fmt, ...)
     }                                                                                                     \
   } while (0)
 
-static std::atomic<long> g_optTable{0}, g_optWarps{0}, g_optChunkMb{0}, g_optIndex{0};
+// C++ exceptions (std::bad_alloc from the host-side vectors) must not cross the extern "C" boundary
+template <class R, class F>
+static R guarded(R onFail, F &&f) noexcept
+{
+  try {
+    return f();
+  } catch (const std::bad_alloc &) {
+    set_err("out of host memory");
+  } catch (...) {
+    set_err("unexpected C++ exception");
+  }
+  return onFail;
+}
+
+static std::atomic<long> g_optTable{0}, g_optWarps{0}, g_optChunkMb{0}, g_optIndex{0}, g_optOverlap{1}, g_optContexts{4};
 
 // hsr_index.cu
 bool hsr_parallel_mt_index(const uint8_t *dIn, uint64_t compLen, uint64_t n, int N, int bits, std::vector<hsr_block_t> *out, float *ms);
@@ -80,6 +98,8 @@ extern "C" int hsr_set_option(const char *key, long value)
   if (!strcmp(key, "warps")) { if (value < 0 || value > 32) return -1; g_optWarps = value; return 0; }
   if (!strcmp(key, "chunk_mb")) { if (value < 0) return -1; g_optChunkMb = value; return 0; }
   if (!strcmp(key, "index")) { if (value < 0 || value > 2) return -1; g_optIndex = value; return 0; }
+  if (!strcmp(key, "overlap")) { if (value < 0 || value > 1) return -1; g_optOverlap = value; return 0; }
+  if (!strcmp(key, "contexts")) { if (value < 1 || value > 16) return -1; g_optContexts = value; return 0; }
   return -1;
 }
 
@@ -90,6 +110,8 @@ extern "C" long hsr_get_option(const char *key)
   if (!strcmp(key, "warps")) return g_optWarps;
   if (!strcmp(key, "chunk_mb")) return g_optChunkMb;
   if (!strcmp(key, "index")) return g_optIndex;
+  if (!strcmp(key, "overlap")) return g_optOverlap;
+  if (!strcmp(key, "contexts")) return g_optContexts;
   return -1;
 }
 
@@ -161,31 +183,37 @@ static bool read_header(int family, int N, const uint8_t *in, size_t inLength, s
 constexpr uint64_t kFillUnit = 4ull << 20; // single-symbol runs are cut into fills of this size
 constexpr uint64_t kMaxUnitIn = 0xfff00000ull; // per-unit compressed bytes must fit the ring's 32-bit cursor
 
-extern "C" long hsr_mt_index(int N, const uint8_t *in, size_t inLength, hsr_block_t *blocks, size_t maxBlocks)
+constexpr uint64_t kMaxDecoded = 1ull << 40; // 1 TiB: bounds the unit count a hostile header can ask for
+
+// One pass over the mt_ header chain (src/mt_rANS32x64_16w_decode.cpp:40-66,94 — the serial walk the reference does on
+// its calling thread). Every unit is handed to `emit`; returns the number of units or -1.
+template <class Emit>
+static long mt_walk(int N, const uint8_t *in, size_t inLength, Emit &&emit, hsr_block_t *lastCodedOut)
 {
   if (!(N == 32 || N == 64)) { set_err("state count must be 32 or 64"); return -1; }
   if (!in || inLength < 16 + 4 * (size_t)N + 512) { set_err("input shorter than the fixed header"); return -1; }
   const uint64_t n = rd64(in);
   if (n < (uint64_t)N) { set_err("decoded length below the state count"); return -1; }
+  if (n > kMaxDecoded) { set_err("decoded length above 1 TiB is not supported"); return -1; }
   const uint64_t outLengthInStates = n - N + 1;
   uint64_t pos = 16, i = 0;
   size_t count = 0;
-  long lastCoded = -1;
-  auto emit = [&](const hsr_block_t &b) {
-    if (blocks && count < maxBlocks) blocks[count] = b;
-    count++;
-  };
+  hsr_block_t pending{}; // the last coded block is held back: a ragged end of the stream becomes its tail
+  bool havePending = false;
+  auto flush = [&]() { if (havePending) { emit(pending, count - 1); havePending = false; } };
   do {
     if (pos + 8 > inLength) { set_err("mt_ chain runs past the input at offset %llu", (unsigned long long)pos); return -1; }
     const uint64_t v = rd64(in + pos);
     if (v >> 63) { // single-symbol run (src/mt_rANS32x64_16w_decode.cpp:46-54)
       const uint64_t size = v & ((1ull << 54) - 1);
       if (size > n - i) { set_err("single-symbol run overruns the decoded length"); return -1; }
+      flush();
       for (uint64_t o = 0; o < size; o += kFillUnit) {
         hsr_block_t b{};
         b.inOffset = pos; b.inEnd = pos + 8; b.outOffset = i + o; b.count = std::min(kFillUnit, size - o);
         b.kind = 1; b.symbol = (uint32_t)(v >> 54) & 0xffu;
-        emit(b);
+        emit(b, count);
+        count++;
       }
       pos += 8;
       i += size;
@@ -204,23 +232,37 @@ extern "C" long hsr_mt_index(int N, const uint8_t *in, size_t inLength, hsr_bloc
       if (!(i + rows * N < outLengthInStates)) after = inLength;
       if (after < pos + 16 + 4 * (uint64_t)N + 512 || after > inLength) { set_err("mt_ skip offset inconsistent"); return -1; }
       if (after - pos > kMaxUnitIn) { set_err("mt_ block larger than 4 GiB compressed is not supported"); return -1; }
-      hsr_block_t b{};
-      b.inOffset = pos + 16; b.inEnd = after; b.outOffset = i; b.count = rows * N; b.kind = 0;
-      lastCoded = (long)count;
-      emit(b);
+      flush();
+      pending = hsr_block_t{};
+      pending.inOffset = pos + 16; pending.inEnd = after; pending.outOffset = i; pending.count = rows * N; pending.kind = 0;
+      havePending = true;
+      count++;
       pos = after;
       i += rows * N;
     }
   } while (i < outLengthInStates);
 
   if (i < n) { // leftover < N symbols use the last coded block's states and cursor (:99-130)
-    if (lastCoded < 0 || (size_t)lastCoded + 1 != count) { set_err("mt_ stream ends in a tail without a coded block"); return -1; }
-    if (blocks && (size_t)lastCoded < maxBlocks) {
-      blocks[lastCoded].tail = (uint32_t)(n - i);
-      blocks[lastCoded].count += n - i;
-    }
+    if (!havePending) { set_err("mt_ stream ends in a tail without a coded block"); return -1; }
+    pending.tail = (uint32_t)(n - i);
+    pending.count += n - i;
   }
+  if (lastCodedOut && havePending) *lastCodedOut = pending;
+  flush();
   return (long)count;
+}
+
+extern "C" long hsr_mt_index(int N, const uint8_t *in, size_t inLength, hsr_block_t *blocks, size_t maxBlocks)
+{
+  return mt_walk(N, in, inLength, [&](const hsr_block_t &b, size_t at) { if (blocks && at < maxBlocks) blocks[at] = b; }, nullptr);
+}
+
+// the same walk into a vector, one pass
+static bool mt_index_vector(int N, const uint8_t *in, size_t inLength, std::vector<hsr_block_t> *out)
+{
+  out->clear();
+  out->reserve((size_t)std::min<uint64_t>(inLength / 32768 + 64, 1u << 22));
+  return mt_walk(N, in, inLength, [&](const hsr_block_t &b, size_t) { out->push_back(b); }, nullptr) >= 0;
 }
 
 extern "C" int hsr_mt_partition(const hsr_block_t *blocks, size_t count, int parts, size_t *firstUnit)
@@ -315,24 +357,72 @@ static bool prepare_kernel(const void *fn, LaunchInfo *li, size_t dynamicSmem = 
   return true;
 }
 
-// launches the units kernel over `numBlocks` records of a device-resident index
+// Launch-private work slots of the units kernels: a ring of {next unit, CTAs that have left} pairs per device, all
+// zero at rest — the last CTA of a launch hands its slot back zeroed (units_leave), so no memset sits between two
+// launches and overlapping launches (programmatic dependent launch, several host threads, several CUDA streams) never
+// share a counter. A units kernel in flight holds at least one resident CTA, and a device holds at most 148 x 32 of
+// them, so 8192 slots cannot wrap onto a launch that is still running.
+constexpr uint32_t kWorkSlots = 8192;
+struct WorkRing {
+  int device = -1;
+  uint32_t *d = nullptr;
+  std::atomic<uint32_t> next{0};
+};
+
+static uint32_t *claim_work_slot()
+{
+  static std::mutex mu;
+  static std::vector<std::unique_ptr<WorkRing>> rings;
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev), return nullptr);
+  WorkRing *r = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto &x : rings)
+      if (x->device == dev) { r = x.get(); break; }
+    if (!r) {
+      std::unique_ptr<WorkRing> x(new WorkRing);
+      x->device = dev;
+      CU_TRY(cudaMalloc(&x->d, kWorkSlots * 2 * sizeof(uint32_t)), return nullptr);
+      CU_TRY(cudaMemset(x->d, 0, kWorkSlots * 2 * sizeof(uint32_t)), return nullptr);
+      rings.push_back(std::move(x));
+      r = rings.back().get();
+    }
+  }
+  return r->d + 2 * (r->next.fetch_add(1, std::memory_order_relaxed) % kWorkSlots);
+}
+
+// launches the units kernel over `numBlocks` records of a device-resident index; status bits are OR-ed into *dStatus
 static int launch_units(int family, int N, int bits, const uint8_t *dIn, uint64_t inBase, uint8_t *dOut, uint64_t outBase,
-                        const hsr_block_t *dBlocks, uint32_t numBlocks, uint32_t *dCounter, cudaStream_t st,
+                        const hsr_block_t *dBlocks, uint32_t numBlocks, uint32_t *dStatus, cudaStream_t st,
                         uint32_t *dStreamStatus = nullptr, uint64_t decodedBytes = 0)
 {
   if (numBlocks == 0) return 0;
   const int table = pick_table(bits, numBlocks, decodedBytes);
   const KernelEntry &ke = kernel_entry(family, N, bits, table);
-  DecodeParams p{dIn, inBase, dOut, outBase, dBlocks, numBlocks, dCounter, dStreamStatus};
+  uint32_t *dWork = claim_work_slot();
+  if (!dWork) return -1;
+  DecodeParams p{dIn, inBase, dOut, outBase, dBlocks, numBlocks, dWork, dStatus, dStreamStatus};
   void *args[] = {&p};
-  CU_TRY(cudaMemsetAsync(dCounter, 0, 4, st), return -1); // work counter only; status bits accumulate
   LaunchInfo li;
   if (!prepare_kernel(ke.units, &li, dynamic_smem(ke))) return -1;
   // persistent one-warp CTAs: every SM filled to its residency limit, units handed out by an atomic counter
   const long optWarps = g_optWarps;
   const uint32_t perSm = optWarps > 0 ? std::min<uint32_t>((uint32_t)optWarps, (uint32_t)li.ctasPerSm) : (uint32_t)li.ctasPerSm;
   const uint32_t grid = std::min<uint32_t>(numBlocks, perSm * (uint32_t)li.smCount);
-  CU_TRY(cudaLaunchKernel(ke.units, dim3(grid), dim3(32), args, dynamic_smem(ke), st), return -1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(32);
+  cfg.dynamicSmemBytes = dynamic_smem(ke);
+  cfg.stream = st;
+  // back-to-back units launches overlap: this one may start while the previous units kernel of the stream drains
+  // (see units_enter in hsr_kernels.cuh); anything else in front of it serialises as usual
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_optOverlap ? 1u : 0u;
+  CU_TRY(cudaLaunchKernelExC(&cfg, ke.units, args), return -1);
   return 1;
 }
 
@@ -444,7 +534,7 @@ struct hsr_stream {
   uint64_t inBase = 0, inBytes = 0;
   std::vector<hsr_block_t> blocks; // this shard's units (absolute offsets)
   hsr_block_t *dBlocks = nullptr;
-  uint32_t *dCounter = nullptr;    // [0] work counter, [1] status
+  uint32_t *dCounter = nullptr;    // [0] work counter of the block_ kernels, [1] status bits of every kernel
   uint64_t outOffset = 0, outBytes = 0;
   uint64_t decodedTotal = 0; // bytes one decode_async produces (table choice)
   double indexMs = 0;
@@ -521,6 +611,8 @@ static bool plan_batch(int family, int N, const uint8_t *inBase, const hsr_batch
   // per-stream header checks (src/rANS32x32_16w.cpp:164-180); bad streams get length 0 and are skipped
   for (size_t i = 0; i < count; i++) {
     const hsr_batch_item_t &it = items[i];
+    // streams are sequences of 16-bit words: an odd offset would make every 16-bit device load of the stream misaligned
+    if (it.inOffset & 1ull) { set_err("stream %zu: inOffset must be even", i); continue; }
     if (!read_header(family, N, inBase + it.inOffset, (size_t)it.inLength, (size_t)it.outCapacity, &bp->hdr[i])) continue;
     if (bp->hdr[i].compLen < fixed_header_bytes(family, N) || bp->hdr[i].compLen > kMaxUnitIn) continue;
     bp->good[i] = 1;
@@ -556,7 +648,7 @@ static bool plan_batch(int family, int N, const uint8_t *inBase, const hsr_batch
   return true;
 }
 
-extern "C" hsr_stream_t *hsr_stream_upload(int family, int N, int bits, const uint8_t *in, size_t inLength, int shard, int shards)
+static hsr_stream_t *stream_upload_impl(int family, int N, int bits, const uint8_t *in, size_t inLength, int shard, int shards)
 {
   g_err.clear();
   if (!valid_codec(family, N, bits)) { set_err("unsupported codec (family %d, N %d, bits %d)", family, N, bits); return nullptr; }
@@ -565,6 +657,7 @@ extern "C" hsr_stream_t *hsr_stream_upload(int family, int N, int bits, const ui
   Header h;
   if (!read_header(family, N, in, inLength, (size_t)-1, &h)) return nullptr;
   if (h.compLen < fixed_header_bytes(family, N)) { set_err("compressed length field too small"); return nullptr; }
+  if (h.n > kMaxDecoded) { set_err("decoded length above 1 TiB is not supported"); return nullptr; }
 
   std::unique_ptr<hsr_stream, void (*)(hsr_stream *)> s(new hsr_stream, stream_release);
   s->family = family; s->N = N; s->bits = bits; s->n = h.n; s->compLen = h.compLen;
@@ -573,10 +666,8 @@ extern "C" hsr_stream_t *hsr_stream_upload(int family, int N, int bits, const ui
   uint64_t lo = 0, hi = h.compLen;
   if (family == HSR_MT) {
     const auto t0 = std::chrono::steady_clock::now();
-    const long cnt = hsr_mt_index(N, in, (size_t)h.compLen, nullptr, 0);
-    if (cnt < 0) return nullptr;
-    std::vector<hsr_block_t> all((size_t)cnt);
-    if (hsr_mt_index(N, in, (size_t)h.compLen, all.data(), all.size()) != cnt) return nullptr;
+    std::vector<hsr_block_t> all;
+    if (!mt_index_vector(N, in, (size_t)h.compLen, &all)) return nullptr;
     s->indexMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     std::vector<size_t> first((size_t)shards + 1);
     hsr_mt_partition(all.data(), all.size(), shards, first.data());
@@ -608,7 +699,8 @@ extern "C" hsr_stream_t *hsr_stream_upload(int family, int N, int bits, const ui
   return s.release();
 }
 
-extern "C" hsr_stream_t *hsr_stream_from_device(int family, int N, int bits, const void *dInV, size_t inLength)
+static hsr_stream_t *stream_from_device_impl(int family, int N, int bits, const void *dInV, size_t inLength, const hsr_block_t *dIndex,
+                                             size_t numUnits)
 {
   g_err.clear();
   if (!valid_codec(family, N, bits)) { set_err("unsupported codec (family %d, N %d, bits %d)", family, N, bits); return nullptr; }
@@ -620,6 +712,8 @@ extern "C" hsr_stream_t *hsr_stream_from_device(int family, int N, int bits, con
   Header h{rd64(hdr), rd64(hdr + 8)};
   if (inLength < h.compLen) { set_err("inLength %zu < compressed length %llu", inLength, (unsigned long long)h.compLen); return nullptr; }
   if (h.n < (uint64_t)N || h.compLen < fixed_header_bytes(family, N)) { set_err("malformed header"); return nullptr; }
+  if (h.n > kMaxDecoded) { set_err("decoded length above 1 TiB is not supported"); return nullptr; }
+  if (dIndex && family != HSR_MT) { set_err("a block index only applies to mt_ streams"); return nullptr; }
 
   std::unique_ptr<hsr_stream, void (*)(hsr_stream *)> s(new hsr_stream, stream_release);
   s->family = family; s->N = N; s->bits = bits; s->n = h.n; s->compLen = h.compLen;
@@ -634,6 +728,26 @@ extern "C" hsr_stream_t *hsr_stream_from_device(int family, int N, int bits, con
   if (is_raw_family(family)) {
     if (h.compLen > kMaxUnitIn) { set_err("raw streams above 4 GiB compressed are not supported"); return nullptr; }
     s->blocks.push_back(raw_unit(family, N, h));
+  } else if (family == HSR_MT && dIndex) {
+    // the producer's own block table (hsr_encode_mt_device_indexed): copied back and checked record by record — every
+    // read and write of the kernels must stay inside [0, compLen) / [0, n) whatever the table claims
+    const auto t0 = std::chrono::steady_clock::now();
+    if (numUnits == 0 || numUnits > (size_t)(h.compLen / 8)) { set_err("implausible unit count"); return nullptr; }
+    s->blocks.resize(numUnits);
+    CU_TRY(cudaMemcpy(s->blocks.data(), dIndex, numUnits * sizeof(hsr_block_t), cudaMemcpyDeviceToHost), return nullptr);
+    uint64_t at = 0;
+    for (size_t k = 0; k < numUnits; k++) {
+      const hsr_block_t &b = s->blocks[k];
+      const bool coded = b.kind == 0;
+      const bool ok = (b.kind == 0 || b.kind == 1) && (b.inOffset & 1ull) == 0 && b.inOffset >= 16 && b.inEnd <= h.compLen &&
+                      b.inOffset + (coded ? 4ull * N + 512 : 8ull) <= b.inEnd && b.inEnd - b.inOffset <= kMaxUnitIn && b.outOffset == at &&
+                      b.count <= h.n - at && b.tail < (uint32_t)N && (coded ? (b.count - b.tail) % (uint64_t)N == 0 && b.count >= b.tail : b.tail == 0) &&
+                      (b.tail == 0 || at + b.count == h.n);
+      if (!ok) { set_err("block index record %zu is inconsistent with the stream", k); return nullptr; }
+      at += b.count;
+    }
+    if (at != h.n) { set_err("block index does not cover the decoded length"); return nullptr; }
+    s->indexMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   } else if (family == HSR_MT) {
     // segment-parallel index first (hsr_index.cu); the serial walk below is the fallback and the error reporter
     const long indexMode = g_optIndex;
@@ -677,8 +791,7 @@ extern "C" hsr_stream_t *hsr_stream_from_device(int family, int N, int bits, con
   return s.release();
 }
 
-extern "C" hsr_stream_t *hsr_stream_upload_batch(int family, int N, int bits, const uint8_t *inBase, const hsr_batch_item_t *items,
-                                                 size_t count)
+static hsr_stream_t *stream_upload_batch_impl(int family, int N, int bits, const uint8_t *inBase, const hsr_batch_item_t *items, size_t count)
 {
   g_err.clear();
   if (!valid_codec(family, N, bits)) { set_err("unsupported codec (family %d, N %d, bits %d)", family, N, bits); return nullptr; }
@@ -711,6 +824,28 @@ extern "C" hsr_stream_t *hsr_stream_upload_batch(int family, int N, int bits, co
   return s.release();
 }
 
+extern "C" hsr_stream_t *hsr_stream_upload(int family, int N, int bits, const uint8_t *in, size_t inLength, int shard, int shards)
+{
+  return guarded<hsr_stream_t *>(nullptr, [&] { return stream_upload_impl(family, N, bits, in, inLength, shard, shards); });
+}
+
+extern "C" hsr_stream_t *hsr_stream_from_device(int family, int N, int bits, const void *dIn, size_t inLength)
+{
+  return guarded<hsr_stream_t *>(nullptr, [&] { return stream_from_device_impl(family, N, bits, dIn, inLength, nullptr, 0); });
+}
+
+extern "C" hsr_stream_t *hsr_stream_from_device_indexed(int N, int bits, const void *dIn, size_t inLength, const hsr_block_t *dIndex, size_t numUnits)
+{
+  if (!dIndex) { set_err("null block index"); return nullptr; }
+  return guarded<hsr_stream_t *>(nullptr, [&] { return stream_from_device_impl(HSR_MT, N, bits, dIn, inLength, dIndex, numUnits); });
+}
+
+extern "C" hsr_stream_t *hsr_stream_upload_batch(int family, int N, int bits, const uint8_t *inBase, const hsr_batch_item_t *items,
+                                                 size_t count)
+{
+  return guarded<hsr_stream_t *>(nullptr, [&] { return stream_upload_batch_impl(family, N, bits, inBase, items, count); });
+}
+
 extern "C" uint64_t hsr_stream_decoded_length(const hsr_stream_t *s) { return s ? s->n : 0; }
 extern "C" uint64_t hsr_stream_shard_out_offset(const hsr_stream_t *s) { return s ? s->outOffset : 0; }
 extern "C" uint64_t hsr_stream_shard_out_bytes(const hsr_stream_t *s) { return s ? s->outBytes : 0; }
@@ -739,7 +874,7 @@ extern "C" int hsr_stream_decode_async(hsr_stream_t *s, void *dOutV, size_t outC
     return launch_block_batch(s->N, s->bits, s->dIn, dOut, s->dDescs, s->numDescs, s->dCounter, nullptr, st, s->decodedTotal);
   if (s->family == HSR_BLOCK)
     return launch_block_stream(s->N, s->bits, s->dIn, s->compLen, dOut, s->n, s->dCounter, st);
-  return launch_units(s->family, s->N, s->bits, s->dIn, s->inBase, dOut, outBase, s->dBlocks, (uint32_t)s->blocks.size(), s->dCounter, st,
+  return launch_units(s->family, s->N, s->bits, s->dIn, s->inBase, dOut, outBase, s->dBlocks, (uint32_t)s->blocks.size(), s->dCounter + 1, st,
                       nullptr, s->decodedTotal);
 }
 
@@ -755,38 +890,82 @@ extern "C" unsigned hsr_stream_status(hsr_stream_t *s)
 
 // ------------------------------------------------------------------------------------------------ host-pointer decode
 
-// Per-device scratch reused across hsr_decode calls: device buffers grow on demand and are kept, like the
-// reference harness keeps its three buffers for the whole run (src/main.cpp:125-127).
+// Scratch of one host-pointer decode in flight: three streams (copy-in, run, copy-out) and device buffers that grow
+// on demand and are kept, like the reference harness keeps its three buffers for the whole run (src/main.cpp:125-127).
+// Every device has a small POOL of these (option "contexts", default 4): the reference's decoders are re-entrant and
+// are called from many threads at once (SURVEY.md §8b "Threading"), so K host threads decoding K streams each lease
+// their own context and their copies and kernels overlap on the device; only a K+1-th caller waits.
 struct DeviceCtx {
-  std::mutex mu;
   int device = -1;
+  bool busy = false;
   cudaStream_t sIn = nullptr, sRun = nullptr, sOut = nullptr;
   uint8_t *dIn = nullptr; size_t inCap = 0;
   uint8_t *dOut = nullptr; size_t outCap = 0;
   hsr_block_t *dBlocks = nullptr; size_t blocksCap = 0;
   hsr_block_t *hBlocks = nullptr; size_t hBlocksCap = 0; // pinned + mapped: kernels read the index straight from host memory
-  uint32_t *dCounters = nullptr; size_t countersCap = 0; // 4 u32 per chunk: counter, status, pad, pad
+  uint32_t *dCounters = nullptr; size_t countersCap = 0; // 4 u32 per launch: block_ work counter, status, pad, pad
   std::vector<cudaEvent_t> evIn, evRun;
 };
 
-static DeviceCtx *get_ctx(int device)
+struct CtxPool {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<std::unique_ptr<DeviceCtx>> all;
+};
+static CtxPool &ctx_pool()
 {
-  static std::mutex mu;
-  static std::vector<std::unique_ptr<DeviceCtx>> ctxs;
-  std::lock_guard<std::mutex> lock(mu);
-  for (auto &c : ctxs)
-    if (c->device == device) return c.get();
-  std::unique_ptr<DeviceCtx> c(new DeviceCtx);
-  c->device = device;
-  if (cudaStreamCreateWithFlags(&c->sIn, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&c->sRun, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&c->sOut, cudaStreamNonBlocking) != cudaSuccess) {
-    set_err("cannot create CUDA streams: %s", cudaGetErrorString(cudaGetLastError()));
-    return nullptr;
-  }
-  ctxs.push_back(std::move(c));
-  return ctxs.back().get();
+  static CtxPool *p = new CtxPool; // never destroyed: worker threads may still hold leases at process exit
+  return *p;
 }
+
+// RAII lease of an idle context of `device`; creates one while fewer than "contexts" exist, otherwise waits
+class CtxLease {
+ public:
+  explicit CtxLease(int device)
+  {
+    CtxPool &pool = ctx_pool();
+    std::unique_lock<std::mutex> lock(pool.mu);
+    for (;;) {
+      size_t have = 0;
+      for (auto &c : pool.all) {
+        if (c->device != device) continue;
+        have++;
+        if (!c->busy) { c->busy = true; ctx_ = c.get(); return; }
+      }
+      if (have < (size_t)std::max<long>(1, g_optContexts)) {
+        std::unique_ptr<DeviceCtx> c(new DeviceCtx);
+        c->device = device;
+        if (cudaStreamCreateWithFlags(&c->sIn, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->sRun, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->sOut, cudaStreamNonBlocking) != cudaSuccess) {
+          set_err("cannot create CUDA streams: %s", cudaGetErrorString(cudaGetLastError()));
+          return;
+        }
+        c->busy = true;
+        pool.all.push_back(std::move(c));
+        ctx_ = pool.all.back().get();
+        return;
+      }
+      pool.cv.wait(lock);
+    }
+  }
+  ~CtxLease()
+  {
+    if (!ctx_) return;
+    CtxPool &pool = ctx_pool();
+    {
+      std::lock_guard<std::mutex> lock(pool.mu);
+      ctx_->busy = false;
+    }
+    pool.cv.notify_all();
+  }
+  CtxLease(const CtxLease &) = delete;
+  CtxLease &operator=(const CtxLease &) = delete;
+  DeviceCtx *get() const { return ctx_; }
+
+ private:
+  DeviceCtx *ctx_ = nullptr;
+};
 
 template <class T>
 static bool grow(T *&p, size_t &cap, size_t need)
@@ -871,7 +1050,7 @@ static bool run_units_pipelined(DeviceCtx *c, int family, int N, int bits, uint8
   const size_t nRanges = cuts.size() - 1;
 
   if (!grow(c->dOut, c->outCap, (size_t)(outHi - outLo) + 16)) return false;
-  if (!grow(c->dCounters, c->countersCap, nRanges * 4)) return false;
+  if (!grow(c->dCounters, c->countersCap, 4)) return false;
   const hsr_block_t *devBlocks = nullptr; // device-visible address of units[first]
   if (units >= c->hBlocks && units + last <= c->hBlocks + c->hBlocksCap) {
     devBlocks = units + first; // already in the mapped buffer (UVA: same address on the device)
@@ -886,7 +1065,7 @@ static bool run_units_pipelined(DeviceCtx *c, int family, int N, int bits, uint8
     c->evRun.push_back(e);
   }
 
-  CU_TRY(cudaMemsetAsync(c->dCounters, 0, nRanges * 16, c->sRun), return false);
+  CU_TRY(cudaMemsetAsync(c->dCounters, 0, 16, c->sRun), return false); // [1]: status bits, OR over every range
 
   size_t piece = 0;
   for (size_t r = 0; r < nRanges; r++) {
@@ -896,7 +1075,7 @@ static bool run_units_pipelined(DeviceCtx *c, int family, int N, int bits, uint8
     CU_TRY(cudaStreamWaitEvent(c->sRun, c->evIn[piece], 0), return false);
     uint64_t rangeDecoded = 0;
     for (size_t k = a; k < b; k++) rangeDecoded += units[k].count;
-    if (launch_units(family, N, bits, c->dIn, fl.lo, c->dOut, outLo, devBlocks + (a - first), (uint32_t)(b - a), c->dCounters + 4 * r, c->sRun,
+    if (launch_units(family, N, bits, c->dIn, fl.lo, c->dOut, outLo, devBlocks + (a - first), (uint32_t)(b - a), c->dCounters + 1, c->sRun,
                      nullptr, rangeDecoded) < 0)
       return false;
     CU_TRY(cudaEventRecord(c->evRun[r], c->sRun), return false);
@@ -904,14 +1083,12 @@ static bool run_units_pipelined(DeviceCtx *c, int family, int N, int bits, uint8
     const uint64_t oLo = units[a].outOffset, oHi = units[b - 1].outOffset + units[b - 1].count;
     CU_TRY(cudaMemcpyAsync(out + oLo, c->dOut + (oLo - outLo), (size_t)(oHi - oLo), cudaMemcpyDeviceToHost, c->sOut), return false);
   }
-  std::vector<uint32_t> status(nRanges * 4);
-  CU_TRY(cudaMemcpyAsync(status.data(), c->dCounters, nRanges * 16, cudaMemcpyDeviceToHost, c->sOut), return false);
+  uint32_t status[4] = {0, 0, 0, 0};
+  CU_TRY(cudaMemcpyAsync(status, c->dCounters, 16, cudaMemcpyDeviceToHost, c->sOut), return false);
   CU_TRY(cudaStreamSynchronize(c->sOut), return false);
   CU_TRY(cudaStreamSynchronize(c->sIn), return false);
   CU_TRY(cudaStreamSynchronize(c->sRun), return false);
-  uint32_t bad = 0;
-  for (size_t r = 0; r < nRanges; r++) bad |= status[4 * r + 1];
-  if (bad) { set_err("malformed stream (device status 0x%x)", bad); return false; }
+  if (status[1]) { set_err("malformed stream (device status 0x%x)", status[1]); return false; }
   return true;
 }
 
@@ -921,9 +1098,9 @@ static bool decode_units_from_host(int device, int family, int N, int bits, cons
 {
   if (first >= last) return true;
   CU_TRY(cudaSetDevice(device), return false);
-  DeviceCtx *c = get_ctx(device);
+  CtxLease lease(device);
+  DeviceCtx *c = lease.get();
   if (!c) return false;
-  std::lock_guard<std::mutex> lock(c->mu);
   InFlight fl;
   if (!start_h2d(c, in, units[first].inOffset & ~15ull, units[last - 1].inEnd, &fl)) return false;
   return run_units_pipelined(c, family, N, bits, out, units, first, last, fl);
@@ -932,9 +1109,9 @@ static bool decode_units_from_host(int device, int family, int N, int bits, cons
 static bool decode_block_from_host(int device, int N, int bits, const uint8_t *in, const Header &h, uint8_t *out)
 {
   CU_TRY(cudaSetDevice(device), return false);
-  DeviceCtx *c = get_ctx(device);
+  CtxLease lease(device);
+  DeviceCtx *c = lease.get();
   if (!c) return false;
-  std::lock_guard<std::mutex> lock(c->mu);
   if (!grow(c->dIn, c->inCap, (size_t)h.compLen + 16)) return false;
   if (!grow(c->dOut, c->outCap, (size_t)h.n + 16)) return false;
   if (!grow(c->dCounters, c->countersCap, 4)) return false;
@@ -949,7 +1126,7 @@ static bool decode_block_from_host(int device, int N, int bits, const uint8_t *i
   return true;
 }
 
-extern "C" size_t hsr_decode(int family, int N, int bits, const uint8_t *in, size_t inLength, uint8_t *out, size_t outCapacity)
+static size_t decode_impl(int family, int N, int bits, const uint8_t *in, size_t inLength, uint8_t *out, size_t outCapacity)
 {
   g_err.clear();
   if (!valid_codec(family, N, bits)) { set_err("unsupported codec (family %d, N %d, bits %d)", family, N, bits); return 0; }
@@ -968,9 +1145,9 @@ extern "C" size_t hsr_decode(int family, int N, int bits, const uint8_t *in, siz
     return decode_units_from_host(device, family, N, bits, in, out, &u, 0, 1) ? (size_t)h.n : 0;
   }
   // mt_: start moving the whole stream to the device, walk the header chain on the host meanwhile
-  DeviceCtx *c = get_ctx(device);
+  CtxLease lease(device);
+  DeviceCtx *c = lease.get();
   if (!c) return 0;
-  std::lock_guard<std::mutex> lock(c->mu);
   InFlight fl;
   if (!start_h2d(c, in, 0, h.compLen, &fl)) return 0;
   if (!grow_host_blocks(c, (size_t)std::max<uint64_t>(64, h.n / 32768 + 64))) return 0;
@@ -986,25 +1163,30 @@ extern "C" size_t hsr_decode(int family, int N, int bits, const uint8_t *in, siz
   return run_units_pipelined(c, family, N, bits, out, c->hBlocks, 0, (size_t)cnt, fl) ? (size_t)h.n : 0;
 }
 
+extern "C" size_t hsr_decode(int family, int N, int bits, const uint8_t *in, size_t inLength, uint8_t *out, size_t outCapacity)
+{
+  return guarded<size_t>(0, [&] { return decode_impl(family, N, bits, in, inLength, out, outCapacity); });
+}
+
 // Many independent streams of one codec in ONE launch: raw and block_ streams are a single recurrence each (one
 // warp), so a batch is the only way they fill a GPU; mt_ streams simply contribute all their blocks.
-extern "C" size_t hsr_decode_batch(int family, int N, int bits, const uint8_t *inBase, uint8_t *outBase, const hsr_batch_item_t *items,
-                                   size_t count, uint64_t *decodedLengths)
+static size_t decode_batch_impl(int family, int N, int bits, const uint8_t *inBase, uint8_t *outBase, const hsr_batch_item_t *items,
+                                size_t count, uint64_t *decodedLengths)
 {
   g_err.clear();
   if (!valid_codec(family, N, bits)) { set_err("unsupported codec (family %d, N %d, bits %d)", family, N, bits); return 0; }
   if (!inBase || !outBase || !items || !decodedLengths) { set_err("null argument"); return 0; }
   if (count == 0) return 0;
   if (count > 0x7fffffffull) { set_err("too many streams"); return 0; }
+  for (size_t i = 0; i < count; i++) decodedLengths[i] = 0; // every early return below leaves "nothing decoded"
   int device = 0;
   CU_TRY(cudaGetDevice(&device), return 0);
-  DeviceCtx *c = get_ctx(device);
+  CtxLease lease(device);
+  DeviceCtx *c = lease.get();
   if (!c) return 0;
-  std::lock_guard<std::mutex> lock(c->mu);
 
   BatchPlan plan;
   if (!plan_batch(family, N, inBase, items, count, &plan)) return 0;
-  for (size_t i = 0; i < count; i++) decodedLengths[i] = 0;
   std::vector<Header> &hdr = plan.hdr;
   std::vector<char> &good = plan.good;
   std::vector<hsr_block_t> &units = plan.units;
@@ -1014,7 +1196,7 @@ extern "C" size_t hsr_decode_batch(int family, int N, int bits, const uint8_t *i
 
   if (!grow(c->dIn, c->inCap, (size_t)(inHi - inLo) + 16)) return 0;
   if (!grow(c->dOut, c->outCap, (size_t)(outHi - outLo) + 16)) return 0;
-  if (!grow(c->dCounters, c->countersCap, 4 + count)) return 0; // [0] counter, [1] status, [4..] per-stream status
+  if (!grow(c->dCounters, c->countersCap, 4 + count)) return 0; // [0] block_ work counter, [1] status, [4..] per-stream status
   uint32_t *dStreamStatus = c->dCounters + 4;
   CU_TRY(cudaMemsetAsync(c->dCounters, 0, (4 + count) * sizeof(uint32_t), c->sRun), return 0);
   CU_TRY(cudaMemcpyAsync(c->dIn, inBase + inLo, (size_t)(inHi - inLo), cudaMemcpyHostToDevice, c->sRun), return 0);
@@ -1034,7 +1216,7 @@ extern "C" size_t hsr_decode_batch(int family, int N, int bits, const uint8_t *i
     CU_TRY(cudaMemcpyAsync(c->dBlocks, units.data(), units.size() * sizeof(hsr_block_t), cudaMemcpyHostToDevice, c->sRun), return 0);
     uint64_t batchDecoded = 0;
     for (const auto &u : units) batchDecoded += u.count;
-    if (launch_units(family, N, bits, c->dIn, inLo, c->dOut, outLo, c->dBlocks, (uint32_t)units.size(), c->dCounters, c->sRun, dStreamStatus,
+    if (launch_units(family, N, bits, c->dIn, inLo, c->dOut, outLo, c->dBlocks, (uint32_t)units.size(), c->dCounters + 1, c->sRun, dStreamStatus,
                      batchDecoded) < 0)
       return 0;
   }
@@ -1072,8 +1254,58 @@ extern "C" size_t hsr_decode_batch(int family, int N, int bits, const uint8_t *i
   return ok;
 }
 
-extern "C" size_t hsr_decode_mt_multi(int N, int bits, const uint8_t *in, size_t inLength, uint8_t *out, size_t outCapacity,
-                                      const int *devices, int deviceCount)
+extern "C" size_t hsr_decode_batch(int family, int N, int bits, const uint8_t *inBase, uint8_t *outBase, const hsr_batch_item_t *items,
+                                   size_t count, uint64_t *decodedLengths)
+{
+  return guarded<size_t>(0, [&] { return decode_batch_impl(family, N, bits, inBase, outBase, items, count, decodedLengths); });
+}
+
+// ------------------------------------------------------------------------------------------------ one process, many GPUs
+
+// Persistent host threads for hsr_decode_mt_multi (one per device shard in flight; they outlive the call, so a call
+// costs a queue hand-off, not a thread creation per device).
+class ShardWorkers {
+ public:
+  void submit(std::function<void()> f)
+  {
+    std::unique_lock<std::mutex> lock(mu_);
+    queue_.push_back(std::move(f));
+    if (idle_ == 0 && threads_ < 64) {
+      threads_++;
+      std::thread([this] { loop(); }).detach();
+    }
+    lock.unlock();
+    cv_.notify_one();
+  }
+
+ private:
+  void loop()
+  {
+    std::unique_lock<std::mutex> lock(mu_);
+    for (;;) {
+      idle_++;
+      cv_.wait(lock, [this] { return !queue_.empty(); });
+      idle_--;
+      std::function<void()> f = std::move(queue_.front());
+      queue_.pop_front();
+      lock.unlock();
+      f();
+      lock.lock();
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::function<void()>> queue_;
+  int idle_ = 0, threads_ = 0;
+};
+static ShardWorkers &shard_workers()
+{
+  static ShardWorkers *w = new ShardWorkers; // leaked on purpose: its threads are detached
+  return *w;
+}
+
+static size_t decode_mt_multi_impl(int N, int bits, const uint8_t *in, size_t inLength, uint8_t *out, size_t outCapacity,
+                                   const int *devices, int deviceCount)
 {
   g_err.clear();
   if (!valid_codec(HSR_MT, N, bits)) { set_err("unsupported codec (N %d, bits %d)", N, bits); return 0; }
@@ -1081,28 +1313,67 @@ extern "C" size_t hsr_decode_mt_multi(int N, int bits, const uint8_t *in, size_t
   Header h;
   if (!read_header(HSR_MT, N, in, inLength, outCapacity, &h)) return 0;
   if (!out) { set_err("null output"); return 0; }
-  const long cnt = hsr_mt_index(N, in, (size_t)h.compLen, nullptr, 0);
-  if (cnt < 0) return 0;
-  std::vector<hsr_block_t> units((size_t)cnt);
-  if (hsr_mt_index(N, in, (size_t)h.compLen, units.data(), units.size()) != cnt) return 0;
-  std::vector<size_t> first((size_t)deviceCount + 1);
-  hsr_mt_partition(units.data(), units.size(), deviceCount, first.data());
 
-  int prev = 0;
-  cudaGetDevice(&prev);
-  std::vector<std::thread> workers;
-  std::vector<std::string> errors((size_t)deviceCount);
-  std::vector<char> ok((size_t)deviceCount, 0);
-  for (int d = 0; d < deviceCount; d++) {
-    workers.emplace_back([&, d]() {
+  // ONE walk of the header chain (the reference's serial walk, src/mt_rANS32x64_16w_decode.cpp:137-265). Shards are
+  // contiguous unit ranges balanced on compressed + decoded bytes; a shard is handed to its device the moment the walk
+  // has passed its last unit, so device 0 is copying after 1/deviceCount of the walk instead of after two full walks.
+  struct Shard {
+    std::vector<hsr_block_t> units;
+    std::string error;
+    bool ok = true;
+  };
+  std::vector<Shard> shards((size_t)deviceCount);
+  std::mutex mu;
+  std::condition_variable cv;
+  int pending = 0;
+  auto dispatch = [&](int d) {
+    if (shards[(size_t)d].units.empty()) return;
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      pending++;
+    }
+    shard_workers().submit([&, d] {
+      Shard &sh = shards[(size_t)d];
       const int dev = devices ? devices[d] : d;
-      ok[d] = decode_units_from_host(dev, HSR_MT, N, bits, in, out, units.data(), first[d], first[d + 1]);
-      if (!ok[d]) errors[d] = g_err;
+      sh.ok = decode_units_from_host(dev, HSR_MT, N, bits, in, out, sh.units.data(), 0, sh.units.size());
+      if (!sh.ok) sh.error = g_err;
+      {
+        std::lock_guard<std::mutex> lock(mu);
+        pending--;
+      }
+      cv.notify_all();
     });
+  };
+  const uint64_t total = h.compLen + h.n;
+  int cur = 0;
+  uint64_t acc = 0;
+  const long cnt = mt_walk(N, in, (size_t)h.compLen, [&](const hsr_block_t &b, size_t) {
+    const uint64_t w = (b.inEnd - b.inOffset) + b.count;
+    while (cur + 1 < deviceCount && acc + w / 2 > total / (uint64_t)deviceCount * (uint64_t)(cur + 1)) {
+      dispatch(cur);
+      cur++;
+    }
+    shards[(size_t)cur].units.push_back(b);
+    acc += w;
+  }, nullptr);
+  if (cnt >= 0)
+    for (; cur < deviceCount; cur++) dispatch(cur);
+  {
+    std::unique_lock<std::mutex> lock(mu);
+    cv.wait(lock, [&] { return pending == 0; });
   }
-  for (auto &w : workers) w.join();
-  cudaSetDevice(prev);
+  if (cnt < 0) return 0; // shards already dispatched wrote only bytes of well-formed blocks; the call still fails
   for (int d = 0; d < deviceCount; d++)
-    if (!ok[d]) { set_err("device shard %d: %s", d, errors[d].c_str()); return 0; }
+    if (!shards[(size_t)d].ok) { set_err("device shard %d: %s", d, shards[(size_t)d].error.c_str()); return 0; }
   return (size_t)h.n;
+}
+
+extern "C" size_t hsr_decode_mt_multi(int N, int bits, const uint8_t *in, size_t inLength, uint8_t *out, size_t outCapacity,
+                                      const int *devices, int deviceCount)
+{
+  int prev = 0;
+  const bool havePrev = cudaGetDevice(&prev) == cudaSuccess;
+  const size_t r = guarded<size_t>(0, [&] { return decode_mt_multi_impl(N, bits, in, inLength, out, outCapacity, devices, deviceCount); });
+  if (havePrev) cudaSetDevice(prev);
+  return r;
 }

@@ -264,13 +264,26 @@ __device__ __forceinline__ void st_u16(uint8_t *p, uint32_t v) { *reinterpret_ca
 
 template <int N>
 __global__ void __launch_bounds__(256, 8) enc_assemble_kernel(EncPlan pl, const uint16_t *counts, const uint8_t *scratch, const EncBlockMeta *meta,
-                                                           const uint64_t *offsets, uint8_t *out)
+                                                           const uint64_t *offsets, uint8_t *out, hsr_block_t *index)
 {
   const uint32_t tid = threadIdx.x;
   constexpr uint32_t kHeader = 16 + 4 * N + 512;
   for (uint32_t k = blockIdx.x; k < pl.numBlocks; k += gridDim.x) {
     const uint64_t off = offsets[k];
     const uint32_t wordBytes = meta[k].wordBytes;
+    if (index && tid == 0) { // the decoder's unit record of this block: what hsr_mt_index would find by walking the chain
+      const uint64_t begin = block_begin(pl, k), end = block_end(pl, k);
+      hsr_block_t b{};
+      b.outOffset = begin;
+      b.count = end - begin;
+      if (block_is_run(pl, k)) {
+        b.inOffset = off; b.inEnd = off + 8; b.kind = 1; b.symbol = (pl.kinds[k] >> 8) & 0xffu;
+      } else {
+        b.inOffset = off + 16; b.inEnd = offsets[k + 1]; b.kind = 0;
+        b.tail = (uint32_t)((end - begin) % (uint64_t)N); // non-zero only for the block that reaches a ragged end
+      }
+      index[k] = b;
+    }
     uint8_t *dst = out + off; // only 2-byte aligned from here on (src/mt_rANS32x64_16w_decode.cpp:43,57,64)
     if (k == 0 && tid < 8) { // stream header (:363-379)
       const uint64_t v = tid < 4 ? pl.n : offsets[pl.numBlocks];
@@ -566,12 +579,14 @@ extern "C" size_t hsr_encode_mt_bound(int N, size_t length, size_t blockSize)
 
 // Device-pointer encode. dOut must hold hsr_encode_mt_bound() bytes (or at least the actual stream, checked after
 // the scan); returns the compressed length, 0 on error. Synchronises the stream once to learn that length.
-extern "C" size_t hsr_encode_mt_device(int N, int bits, const void *dInV, size_t length, void *dOutV, size_t outCapacity, size_t blockSize,
-                                       void *cudaStream)
+static size_t encode_fixed_device(int N, int bits, const void *dInV, size_t length, void *dOutV, size_t outCapacity, size_t blockSize,
+                                  hsr_block_t *dIndex, size_t indexCapacity, size_t *numUnits, void *cudaStream)
 {
   if (!(N == 32 || N == 64) || bits < 10 || bits > 15 || !dInV || !dOutV) return 0;
   EncPlan pl;
   if (!make_plan(N, length, blockSize, &pl)) return 0;
+  if (dIndex && indexCapacity < pl.numBlocks) return 0;
+  if (numUnits) *numUnits = pl.numBlocks;
   cudaStream_t st = static_cast<cudaStream_t>(cudaStream);
   const uint8_t *dIn = static_cast<const uint8_t *>(dInV);
   uint8_t *dOut = static_cast<uint8_t *>(dOutV);
@@ -598,18 +613,24 @@ extern "C" size_t hsr_encode_mt_device(int N, int bits, const void *dInV, size_t
     return 0;
   }
   if (total > outCapacity) return 0;
-  if (N == 32) enc_assemble_kernel<32><<<gridH, 256, 0, st>>>(pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dOffsets, dOut);
-  else enc_assemble_kernel<64><<<gridH, 256, 0, st>>>(pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dOffsets, dOut);
+  if (N == 32) enc_assemble_kernel<32><<<gridH, 256, 0, st>>>(pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dOffsets, dOut, dIndex);
+  else enc_assemble_kernel<64><<<gridH, 256, 0, st>>>(pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dOffsets, dOut, dIndex);
   if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return 0;
   return (size_t)total;
+}
+
+extern "C" size_t hsr_encode_mt_device(int N, int bits, const void *dIn, size_t length, void *dOut, size_t outCapacity, size_t blockSize,
+                                       void *cudaStream)
+{
+  return encode_fixed_device(N, bits, dIn, length, dOut, outCapacity, blockSize, nullptr, 0, nullptr, cudaStream);
 }
 
 // Block-split policy on the device. Same stream format; blocks are whole numbers of 64 KiB
 // segments chosen by the reference's cost model (see enc_policy_kernel), at most maxBlockSize bytes each (0 = 256 KiB;
 // a multiple of 65536, at most 2^25 = the reference's MaxBlockSize), and stretches of one repeated byte become
 // 8-byte run blocks. Every block is still encoded from fresh states, so the result stays independent GPU work.
-extern "C" size_t hsr_encode_mt_policy_device(int N, int bits, const void *dInV, size_t length, void *dOutV, size_t outCapacity,
-                                              size_t maxBlockSize, void *cudaStream)
+static size_t encode_policy_device(int N, int bits, const void *dInV, size_t length, void *dOutV, size_t outCapacity, size_t maxBlockSize,
+                                   hsr_block_t *dIndex, size_t indexCapacity, size_t *numUnits, void *cudaStream)
 {
   if (!(N == 32 || N == 64) || bits < 10 || bits > 15 || !dInV || !dOutV || length < (size_t)N) return 0;
   if (maxBlockSize == 0) maxBlockSize = 4 * (size_t)kSegBytes;
@@ -644,6 +665,8 @@ extern "C" size_t hsr_encode_mt_policy_device(int N, int bits, const void *dInV,
     (void)cudaGetLastError();
     return 0;
   }
+  if (dIndex && indexCapacity < numBlocks) return 0;
+  if (numUnits) *numUnits = numBlocks;
   EncPlan pl{};
   pl.n = length; pl.blockSize = 0; pl.numBlocks = numBlocks; pl.lastStart = 0; pl.slotBytes = 0;
   pl.starts = sc.dStarts; pl.kinds = sc.dKinds; pl.slotPad = slotPad;
@@ -660,10 +683,34 @@ extern "C" size_t hsr_encode_mt_policy_device(int N, int bits, const void *dInV,
     return 0;
   }
   if (total > outCapacity) return 0;
-  if (N == 32) enc_assemble_kernel<32><<<gridH, 256, 0, st>>>(pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dOffsets, dOut);
-  else enc_assemble_kernel<64><<<gridH, 256, 0, st>>>(pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dOffsets, dOut);
+  if (N == 32) enc_assemble_kernel<32><<<gridH, 256, 0, st>>>(pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dOffsets, dOut, dIndex);
+  else enc_assemble_kernel<64><<<gridH, 256, 0, st>>>(pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dOffsets, dOut, dIndex);
   if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return 0;
   return (size_t)total;
+}
+
+extern "C" size_t hsr_encode_mt_policy_device(int N, int bits, const void *dIn, size_t length, void *dOut, size_t outCapacity,
+                                              size_t maxBlockSize, void *cudaStream)
+{
+  return encode_policy_device(N, bits, dIn, length, dOut, outCapacity, maxBlockSize, nullptr, 0, nullptr, cudaStream);
+}
+
+// The encoder knows where it put every block: with dIndex (device memory, room for hsr_encode_mt_index_bound()
+// records) it also writes the decoder's unit table, one record per block in chain order, so that
+// hsr_stream_from_device_indexed() can wrap the stream without walking the header chain again.
+extern "C" size_t hsr_encode_mt_device_indexed(int N, int bits, const void *dIn, size_t length, void *dOut, size_t outCapacity, size_t blockSize,
+                                               int policy, hsr_block_t *dIndex, size_t indexCapacity, size_t *numUnits, void *cudaStream)
+{
+  if (!dIndex || !numUnits) return 0;
+  return policy ? encode_policy_device(N, bits, dIn, length, dOut, outCapacity, blockSize, dIndex, indexCapacity, numUnits, cudaStream)
+                : encode_fixed_device(N, bits, dIn, length, dOut, outCapacity, blockSize, dIndex, indexCapacity, numUnits, cudaStream);
+}
+
+extern "C" size_t hsr_encode_mt_index_bound(int N, size_t length, size_t blockSize)
+{
+  EncPlan pl;
+  if (!(N == 32 || N == 64) || !make_plan(N, length, blockSize ? blockSize : 65536, &pl)) return 0;
+  return (size_t)pl.numBlocks + 1; // policy mode merges 64 KiB segments, so the fixed 64 KiB count bounds it too
 }
 
 // Host-pointer form with the reference's encoder signature plus the maximum block size.

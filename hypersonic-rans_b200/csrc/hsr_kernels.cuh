@@ -14,7 +14,8 @@ struct DecodeParams {
   uint64_t outBase;
   const hsr_block_t *blocks;
   uint32_t numBlocks;
-  uint32_t *counter;      // [0] work counter, [1] status bits (OR over all units)
+  uint32_t *work;         // this launch's slot of the device's ring: [0] next unit to claim, [1] CTAs that have left
+  uint32_t *status;       // status bits (OR over all units)
   uint32_t *streamStatus; // optional: status bits per stream, indexed by hsr_block_t::reserved (batch decode)
 };
 
@@ -34,13 +35,36 @@ struct BlockStreamParams {
   uint32_t *streamStatus; // optional, per stream
 };
 
-__device__ __forceinline__ void raise(uint32_t *counter, uint32_t *streamStatus, uint32_t stream, uint32_t bits, uint32_t lane)
+__device__ __forceinline__ void raise(uint32_t *status, uint32_t *streamStatus, uint32_t stream, uint32_t bits, uint32_t lane)
 {
   if (lane == 0) {
-    atomicOr(counter + 1, bits);
+    atomicOr(status, bits);
     if (streamStatus)
       atomicOr(streamStatus + stream, bits);
   }
+}
+
+// Units kernels overlap back to back (programmatic dependent launch): every CTA releases the NEXT launch of the stream
+// as its first instruction, so that launch's CTAs take over SM slots one by one as this grid's persistent warps run out
+// of units — the drain of one decode (a last, partial round of the grid: ~6 % of a 15 k-block step, most of a step that
+// has fewer blocks than the GPU has warp slots) is filled with the start of the next. Units kernels never read what
+// another units kernel wrote, so nothing waits at the start; a CTA waits for the previous grid only right before it
+// exits, which keeps completion in stream order. Launches whose predecessor in the stream is anything else (a copy, a
+// memset, a foreign kernel) serialise as usual.
+__device__ __forceinline__ void units_enter() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// The work counter is a launch-private slot of a ring in device memory ({next unit, CTAs that have left}); the last CTA
+// to leave hands the slot back zeroed, so no memset sits between two launches and launches in flight never share one.
+__device__ __forceinline__ void units_leave(uint32_t *work, uint32_t lane)
+{
+  if (lane == 0) {
+    const uint32_t left = atomicAdd(work + 1, 1u);
+    if (left + 1u == gridDim.x) {
+      atomicExch(work, 0u);
+      atomicExch(work + 1, 0u);
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------- mt_ / raw
@@ -71,19 +95,20 @@ __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
   // trip hides behind the decode. Near the end (less than two rounds of the grid left) units are claimed only when a
   // warp is free: a warp that sat on a pre-claimed unit would leave others idle — with as many units as CTAs (a
   // batch of raw streams) the early CTAs would take two units each and the late ones none.
+  units_enter();
   uint32_t claimed = 0;
   bool ahead = true;
   if (lane == 0)
-    claimed = atomicAdd(p.counter, 1u);
+    claimed = atomicAdd(p.work, 1u);
   for (;;) {
     if (!ahead && lane == 0)
-      claimed = atomicAdd(p.counter, 1u);
+      claimed = atomicAdd(p.work, 1u);
     const uint32_t b = __shfl_sync(kFull, claimed, 0);
     if (b >= p.numBlocks)
       break;
     ahead = (uint64_t)b + 2ull * gridDim.x < p.numBlocks;
     if (ahead && lane == 0)
-      claimed = atomicAdd(p.counter, 1u);
+      claimed = atomicAdd(p.work, 1u);
 
     const hsr_block_t *blk = p.blocks + b;
     const uint64_t inOffset = __ldg(&blk->inOffset);
@@ -121,7 +146,7 @@ __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
     if (!info.ok) {
       ring.start_wait();
       ring.drain();
-      raise(p.counter, p.streamStatus, streamId, HSR_ERR_HIST, lane);
+      raise(p.status, p.streamStatus, streamId, HSR_ERR_HIST, lane);
       continue;
     }
     ring.start_wait();
@@ -133,12 +158,13 @@ __device__ __forceinline__ void units_kernel_body(const DecodeParams &p)
       dec.tail(x0, x1, ring, outLane + rows * N, lanePos, tailCount, lane, ltMask);
     ring.drain();
     if (ring.cursor() > ring.glimit)
-      raise(p.counter, p.streamStatus, streamId, HSR_ERR_OVERRUN, lane);
+      raise(p.status, p.streamStatus, streamId, HSR_ERR_OVERRUN, lane);
 #if HSR_RING_TMA
     if (ring.stuck)
-      raise(p.counter, p.streamStatus, streamId, HSR_ERR_INTERNAL, lane);
+      raise(p.status, p.streamStatus, streamId, HSR_ERR_INTERNAL, lane);
 #endif
   }
+  units_leave(p.work, lane);
 }
 
 // ---------------------------------------------------------------------------------------------- block_
@@ -174,7 +200,7 @@ __device__ __forceinline__ void block_stream_decode(const BlockStreamParams &p, 
 
   do {
     if (pos + 8 > d.inLength) {
-      raise(p.counter, p.streamStatus, streamId, HSR_ERR_OVERRUN, lane);
+      raise(p.counter + 1, p.streamStatus, streamId, HSR_ERR_OVERRUN, lane);
       return;
     }
     const uint64_t v = ldg_u64_a2(in + pos);
@@ -183,19 +209,19 @@ __device__ __forceinline__ void block_stream_decode(const BlockStreamParams &p, 
       const uint32_t symbol = (uint32_t)(v >> 54) & 0xffu;
       const uint64_t size = v & ((1ull << 54) - 1);
       if (size > n - i) {
-        raise(p.counter, p.streamStatus, streamId, HSR_ERR_BOUNDS, lane);
+        raise(p.counter + 1, p.streamStatus, streamId, HSR_ERR_BOUNDS, lane);
         return;
       }
       warp_fill(outBase + i, symbol, size, lane);
       i += size;
     } else {
       if (pos + 512 > d.inLength) {
-        raise(p.counter, p.streamStatus, streamId, HSR_ERR_OVERRUN, lane);
+        raise(p.counter + 1, p.streamStatus, streamId, HSR_ERR_OVERRUN, lane);
         return;
       }
       info = build_tables<BITS, N, TK>(sw, in + pos, lane); // :69-76
       if (!info.ok) {
-        raise(p.counter, p.streamStatus, streamId, HSR_ERR_HIST, lane);
+        raise(p.counter + 1, p.streamStatus, streamId, HSR_ERR_HIST, lane);
         return;
       }
       haveHist = true;
@@ -205,7 +231,7 @@ __device__ __forceinline__ void block_stream_decode(const BlockStreamParams &p, 
       if (blockEnd > outLengthInStates)
         blockEnd = outLengthInStates;
       else if (blockEnd & (N - 1)) {
-        raise(p.counter, p.streamStatus, streamId, HSR_ERR_ALIGN, lane);
+        raise(p.counter + 1, p.streamStatus, streamId, HSR_ERR_ALIGN, lane);
         return;
       }
       const uint64_t rows = blockEnd > i ? (blockEnd - i + N - 1) / N : 0;
@@ -218,7 +244,7 @@ __device__ __forceinline__ void block_stream_decode(const BlockStreamParams &p, 
       dec.rows(info, x0, x1, ring, outBase + i + lanePos, rows, lane, ltMask);
       ring.drain();
       if (ring.cursor() > ring.glimit) {
-        raise(p.counter, p.streamStatus, streamId, HSR_ERR_OVERRUN, lane);
+        raise(p.counter + 1, p.streamStatus, streamId, HSR_ERR_OVERRUN, lane);
         return;
       }
       pos = (uint64_t)(ring.gbase - in) + ring.cursor();
@@ -233,7 +259,7 @@ __device__ __forceinline__ void block_stream_decode(const BlockStreamParams &p, 
 
   if (i < n) { // :98-139
     if (!haveHist) {
-      raise(p.counter, p.streamStatus, streamId, HSR_ERR_HIST, lane);
+      raise(p.counter + 1, p.streamStatus, streamId, HSR_ERR_HIST, lane);
       return;
     }
 #if HSR_RING_TMA

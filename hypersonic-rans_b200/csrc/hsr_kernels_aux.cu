@@ -31,7 +31,7 @@ __device__ __forceinline__ bool next_unit(const DecodeParams &p, uint32_t lane, 
 {
   uint32_t b = 0;
   if (lane == 0)
-    b = atomicAdd(p.counter, 1u);
+    b = atomicAdd(p.work, 1u);
   b = __shfl_sync(kFull, b, 0);
   if (b >= p.numBlocks)
     return false;
@@ -73,10 +73,11 @@ __device__ __forceinline__ void raw16_kernel_body(const DecodeParams &p)
   ring.init(sw + L::kOffRing, sw + L::kOffBar, lane);
 #endif
 
+  units_enter();
   UnitView u;
   while (next_unit(p, lane, &u)) {
     if (u.kind != 2u) { // only whole raw streams exist for this codec
-      raise(p.counter, p.streamStatus, u.streamId, HSR_ERR_INTERNAL, lane);
+      raise(p.status, p.streamStatus, u.streamId, HSR_ERR_INTERNAL, lane);
       continue;
     }
     const uint8_t *countsPtr = u.base; // counts, then u32 states[16], then words (src/rANS32x16_16w.cpp:183-203)
@@ -84,7 +85,7 @@ __device__ __forceinline__ void raw16_kernel_body(const DecodeParams &p)
     const uint8_t *words = u.base + 512 + 4 * 16;
     const TableInfo info = build_tables<BITS, 32, TK>(sw, countsPtr, lane);
     if (!info.ok) {
-      raise(p.counter, p.streamStatus, u.streamId, HSR_ERR_HIST, lane);
+      raise(p.status, p.streamStatus, u.streamId, HSR_ERR_HIST, lane);
       continue;
     }
     // idle lanes hold a state that never asks for a word; their lookups stay inside the tables
@@ -128,8 +129,9 @@ __device__ __forceinline__ void raw16_kernel_body(const DecodeParams &p)
     }
     ring.drain();
     if (ring.cursor() > ring.glimit)
-      raise(p.counter, p.streamStatus, u.streamId, HSR_ERR_OVERRUN, lane);
+      raise(p.status, p.streamStatus, u.streamId, HSR_ERR_OVERRUN, lane);
   }
+  units_leave(p.work, lane);
 }
 
 // ---------------------------------------------------------------------------------------------- rANS32x32_32blk_16w
@@ -149,10 +151,11 @@ __device__ __forceinline__ void blk32_kernel_body(const DecodeParams &p)
   Decoder<BITS, 32, TK> dec;
   dec.init(sw);
 
+  units_enter();
   UnitView u;
   while (next_unit(p, lane, &u)) {
     if (u.kind != 3u) {
-      raise(p.counter, p.streamStatus, u.streamId, HSR_ERR_INTERNAL, lane);
+      raise(p.status, p.streamStatus, u.streamId, HSR_ERR_INTERNAL, lane);
       continue;
     }
     const uint8_t *countsPtr = u.base; // counts, u32 states[32], u32 blockSize[31], then the 32 sub-streams (:205-231)
@@ -161,7 +164,7 @@ __device__ __forceinline__ void blk32_kernel_body(const DecodeParams &p)
     const uint8_t *data = sizesPtr + 4 * 31;
     const TableInfo info = build_tables<BITS, 32, TK>(sw, countsPtr, lane);
     if (!info.ok) {
-      raise(p.counter, p.streamStatus, u.streamId, HSR_ERR_HIST, lane);
+      raise(p.status, p.streamStatus, u.streamId, HSR_ERR_HIST, lane);
       continue;
     }
     uint32_t x = ldg_u32_a2(statesPtr + 4 * lane);
@@ -178,7 +181,13 @@ __device__ __forceinline__ void blk32_kernel_body(const DecodeParams &p)
     const uint64_t avail = (uint64_t)(u.end - data);
     const uint64_t startOff = incl - mine;
     if (__any_sync(kFull, startOff > avail)) { // a sub-stream would begin past the end of the stream
-      raise(p.counter, p.streamStatus, u.streamId, HSR_ERR_OVERRUN, lane);
+      raise(p.status, p.streamStatus, u.streamId, HSR_ERR_OVERRUN, lane);
+      continue;
+    }
+    // Sub-streams are sequences of 16-bit words: an odd size field (corrupt header) would make every later read head
+    // odd, and a misaligned 16-bit load is a sticky fault on the GPU where the reference merely reads unaligned.
+    if (__any_sync(kFull, (startOff & 1ull) != 0)) {
+      raise(p.status, p.streamStatus, u.streamId, HSR_ERR_ALIGN, lane);
       continue;
     }
     // Each lane always holds its next TWO words in registers. A renormalisation takes the first, promotes the second
@@ -234,8 +243,9 @@ __device__ __forceinline__ void blk32_kernel_body(const DecodeParams &p)
       renorm(a);
     }
     if (__any_sync(kFull, bad))
-      raise(p.counter, p.streamStatus, u.streamId, HSR_ERR_OVERRUN, lane);
+      raise(p.status, p.streamStatus, u.streamId, HSR_ERR_OVERRUN, lane);
   }
+  units_leave(p.work, lane);
 }
 
 // ---------------------------------------------------------------------------------------------- instantiation

@@ -23,7 +23,8 @@
 extern "C" {
 #endif
 
-#define HSR_VERSION 110 /* 110: + HSR_RAW32BLK, stateCount 16, hsr_encode_mt_policy*, table option 3 */
+#define HSR_VERSION 200 /* 200: + hsr_encode_mt_device_indexed, hsr_stream_from_device_indexed, options "overlap" / "contexts";
+                            overlapping launches, pooled host contexts. 110: + HSR_RAW32BLK, stateCount 16, policy encoder */
 
 /* Stream framings (SURVEY.md §8a "Stream formats"). */
 typedef enum hsr_family {
@@ -48,7 +49,11 @@ const char *hsr_last_error(void);
  *   "warps"      cap on resident one-warp CTAs per SM for the mt_ kernel (1..32, 0 = as many as fit; experiments)
  *   "chunk_mb"   host pipeline chunk size in MiB for hsr_decode on mt_ streams (0 = auto)
  *   "index"      block index of device-resident mt_ streams: 0 = segment-parallel with serial fallback,
- *                1 = serial walk only, 2 = segment-parallel only (fail instead of falling back; tests)         */
+ *                1 = serial walk only, 2 = segment-parallel only (fail instead of falling back; tests)
+ *   "overlap"    1 (default) = consecutive decode launches on one CUDA stream overlap: the next launch's warps take
+ *                over SM slots as the previous launch drains (programmatic dependent launch); 0 = strictly serial
+ *   "contexts"   host-pointer decodes that may be in flight per device at once (1..16, default 4); each holds its
+ *                own streams and device scratch, further callers wait                                              */
 int hsr_set_option(const char *key, long value);
 long hsr_get_option(const char *key);
 
@@ -77,9 +82,11 @@ typedef struct hsr_batch_item {
  * (src/rANS32x16_16w.cpp:162), rANS32x32_32blk_16w_decode_scalar_<b> (src/rans32x32_32blk_16w.cpp:183) and all their AVX variants,
  * block_rANS32xNN_16w_decode_<b> (src/block_rANS32x32_16w_decode.cpp:165-193),
  * mt_rANS32xNN_16w_decode_<b> / _decode_mt_<b> (src/mt_rANS32x64_16w_decode.cpp:301-361).
- * Uses the current CUDA device (hsr_set_device). Re-entrant across threads; one internal context per device.
+ * Uses the current CUDA device (hsr_set_device). Re-entrant like the reference's decoders (SURVEY.md 8b "Threading"):
+ * calls from several host threads run concurrently, each on its own pooled context (option "contexts").
  * Limits: decoded length >= stateCount (below that the reference itself is undefined, src/rANS32x32_16w.cpp:206); a
- * raw stream or a single mt_ block may not exceed 4 GiB of compressed bytes (32-bit word cursor per warp). */
+ * raw stream or a single mt_ block may not exceed 4 GiB of compressed bytes (32-bit word cursor per warp); the
+ * prepared-stream entry points (hsr_stream_*) reject decoded lengths above 1 TiB. */
 size_t hsr_decode(int family, int stateCount, int bits, const uint8_t *pInData, size_t inLength, uint8_t *pOutData,
                   size_t outCapacity);
 /* Same, mt_ only, sharding the block chain over `deviceCount` GPUs of this box from ONE process by contiguous
@@ -94,7 +101,8 @@ int hsr_set_device(int device);
  * (one warp of parallelism, SURVEY.md finding 1), so batching streams is what fills the GPU for those codecs — the
  * analogue of running the reference's decoder on many files from many threads. Stream i occupies
  * inBase[inOffset, inOffset + inLength) and decodes to outBase[outOffset, outOffset + n) with n <= outCapacity;
- * output ranges must not overlap. decodedLengths[i] receives n, or 0 if stream i is malformed (the others are still
+ * inOffset must be even (streams are sequences of 16-bit words; an odd one marks the stream malformed); output ranges
+ * must not overlap. decodedLengths[i] receives n, or 0 if stream i is malformed (the others are still
  * decoded). Returns the number of streams decoded. Each stream is checked like hsr_decode checks its input. */
 
 size_t hsr_decode_batch(int family, int stateCount, int bits, const uint8_t *inBase, uint8_t *outBase,
@@ -139,6 +147,12 @@ hsr_stream_t *hsr_stream_upload(int family, int stateCount, int bits, const uint
  * mt_: the block index is built on the device — K warps each find the first header of their stream segment and
  * walk the chain from there, handing over where they meet (hsr_index.cu); see hsr_stream_index_ms. */
 hsr_stream_t *hsr_stream_from_device(int family, int stateCount, int bits, const void *dIn, size_t inLength);
+/* The same for an mt_ stream whose producer already knows where every block lies (hsr_encode_mt_device_indexed):
+ * dIndex holds numUnits hsr_block_t records in chain order (device memory). The table is copied back and checked
+ * record by record against the stream bounds — nothing it claims can make a kernel read or write out of range —
+ * and the header chain is not walked again. */
+hsr_stream_t *hsr_stream_from_device_indexed(int stateCount, int bits, const void *dIn, size_t inLength, const hsr_block_t *dIndex,
+                                             size_t numUnits);
 /* A batch of independent streams of one codec (see hsr_decode_batch) made resident for repeated decoding. Offsets in
  * `items` are relative to inBase; the decode writes stream i at dOut + items[i].outOffset, so dOut must hold
  * hsr_stream_decoded_length() = max(outOffset + n) bytes. Fails if any stream of the batch is malformed. */
@@ -157,7 +171,11 @@ int hsr_stream_copy_index(const hsr_stream_t *s, hsr_block_t *blocks, size_t max
 /* Launch the decode of the prepared stream into device memory on `cudaStream` (a cudaStream_t, may be NULL).
  * dOut is the base of the WHOLE decoded buffer (shards write at their own offsets) and must hold
  * hsr_stream_decoded_length bytes — or, with HSR_OUT_SHARD_LOCAL, only this shard's bytes.
- * Asynchronous; returns the number of kernels launched (>0) or a negative status. */
+ * Asynchronous; returns the number of kernels launched (0 for a shard that owns no block of the chain) or a negative
+ * status. Any number of decodes of one hsr_stream_t may be in flight, on one CUDA stream or several: every launch
+ * draws a private work counter from a per-device ring. Consecutive launches on one CUDA stream overlap (option
+ * "overlap"): a decode never reads what another decode wrote, so the next one's warps fill the SM slots the previous
+ * one frees while it drains; completion is still in stream order. The status bits are shared by all launches. */
 #define HSR_OUT_SHARD_LOCAL 1u
 int hsr_stream_decode_async(hsr_stream_t *s, void *dOut, size_t outCapacity, unsigned flags, void *cudaStream);
 /* After synchronising: 0 if the last decode saw a well-formed stream, else a bit set of HSR_ERR_*. */
@@ -210,6 +228,14 @@ size_t hsr_encode_mt_policy_device(int stateCount, int bits, const void *dIn, si
                                    size_t maxBlockSize, void *cudaStream);
 /* Hard upper bound of the stream size for `length` input bytes (one 16-bit word per symbol + headers). */
 size_t hsr_encode_mt_bound(int stateCount, size_t length, size_t blockSize);
+/* hsr_encode_mt_device (policy == 0; blockSize as there) or hsr_encode_mt_policy_device (policy != 0; blockSize is its
+ * maxBlockSize) that also hands out what the encoder knows anyway: the decoder's unit table, one hsr_block_t per block
+ * in chain order, written to dIndex (device memory with room for indexCapacity >= hsr_encode_mt_index_bound()
+ * records); *numUnits receives the count. Feed both to hsr_stream_from_device_indexed(). */
+size_t hsr_encode_mt_device_indexed(int stateCount, int bits, const void *dIn, size_t length, void *dOut, size_t outCapacity,
+                                    size_t blockSize, int policy, hsr_block_t *dIndex, size_t indexCapacity, size_t *numUnits,
+                                    void *cudaStream);
+size_t hsr_encode_mt_index_bound(int stateCount, size_t length, size_t blockSize);
 
 /* ------------------------------------------------------------------------------------------------ synthetic inputs */
 
