@@ -7,6 +7,7 @@ Only plumbing lives here: a ctypes binding of ``libhsrans_b200.so`` (``capi``) a
 mirrors the reference's ``_Codecs[]`` table (``codecs``, /root/reference/src/main.cpp:172-236). All decoding
 happens in the hand-written sm_100a kernels under ``csrc/``; there is no Python or CPU decode path.
 """
+from . import capi  # noqa: F401
 from .capi import (  # noqa: F401
     HSR_RAW, HSR_BLOCK, HSR_MT, HSR_RAW32BLK, FAMILY_NAMES, HsrError, Block, PreparedStream, lib, lib_path, version, device_count,
     last_error, set_option, get_option, capacity, host_alloc, HostBuffer, decode, decode_batch, decode_mt_multi, mt_index,

@@ -43,6 +43,8 @@ SIGNATURES = {
     "hsr_decode": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "hsr_decode_mt_multi": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                          C.POINTER(C.c_int), C.c_int]),
+    "hsr_decode_mt_shard": (C.c_size_t, [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                                         C.POINTER(C.c_size_t)]),
     "hsr_set_device": (C.c_int, [C.c_int]),
     "hsr_decode_batch": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "hsr_mt_index": (C.c_long, [C.c_int, C.c_void_p, C.c_size_t, C.POINTER(Block), C.c_size_t]),

@@ -1260,6 +1260,38 @@ extern "C" size_t hsr_decode_batch(int family, int N, int bits, const uint8_t *i
   return guarded<size_t>(0, [&] { return decode_batch_impl(family, N, bits, inBase, outBase, items, count, decodedLengths); });
 }
 
+// One process per GPU: this rank decodes only shard `shard` of `shards` of the chain (the same contiguous block ranges
+// as hsr_stream_upload), from the caller's host buffers, into the caller's full-size output buffer at the shard's own
+// offset. Only the shard's compressed bytes cross PCIe; the header walk covers the whole chain (it is serial).
+static size_t decode_mt_shard_impl(int N, int bits, const uint8_t *in, size_t inLength, uint8_t *out, size_t outCapacity, int shard, int shards,
+                                   size_t *shardOffset)
+{
+  g_err.clear();
+  if (shardOffset) *shardOffset = 0;
+  if (!valid_codec(HSR_MT, N, bits)) { set_err("unsupported codec (N %d, bits %d)", N, bits); return 0; }
+  if (shards < 1 || shard < 0 || shard >= shards) { set_err("bad shard %d of %d", shard, shards); return 0; }
+  Header h;
+  if (!read_header(HSR_MT, N, in, inLength, outCapacity, &h)) return 0;
+  if (!out) { set_err("null output"); return 0; }
+  int device = 0;
+  CU_TRY(cudaGetDevice(&device), return 0);
+  std::vector<hsr_block_t> all;
+  if (!mt_index_vector(N, in, (size_t)h.compLen, &all)) return 0;
+  std::vector<size_t> first((size_t)shards + 1);
+  hsr_mt_partition(all.data(), all.size(), shards, first.data());
+  const size_t a = first[(size_t)shard], b = first[(size_t)shard + 1];
+  if (a >= b) return 0; // this shard owns no block (fewer blocks than shards): nothing to do, no error
+  if (shardOffset) *shardOffset = (size_t)all[a].outOffset;
+  if (!decode_units_from_host(device, HSR_MT, N, bits, in, out, all.data(), a, b)) return 0;
+  return (size_t)(all[b - 1].outOffset + all[b - 1].count - all[a].outOffset);
+}
+
+extern "C" size_t hsr_decode_mt_shard(int N, int bits, const uint8_t *in, size_t inLength, uint8_t *out, size_t outCapacity, int shard,
+                                      int shards, size_t *shardOffset)
+{
+  return guarded<size_t>(0, [&] { return decode_mt_shard_impl(N, bits, in, inLength, out, outCapacity, shard, shards, shardOffset); });
+}
+
 // ------------------------------------------------------------------------------------------------ one process, many GPUs
 
 // Persistent host threads for hsr_decode_mt_multi (one per device shard in flight; they outlive the call, so a call

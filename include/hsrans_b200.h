@@ -95,6 +95,13 @@ size_t hsr_decode(int family, int stateCount, int bits, const uint8_t *pInData, 
 size_t hsr_decode_mt_multi(int stateCount, int bits, const uint8_t *pInData, size_t inLength, uint8_t *pOutData,
                            size_t outCapacity, const int *devices, int deviceCount);
 
+/* One process per GPU: decodes only shard `shard` of `shards` of an mt_ chain — the same contiguous block ranges as
+ * hsr_stream_upload(shard, shards) — on the current device, from the caller's host buffers, into the caller's
+ * full-size output buffer at the shard's own offset (written to *pShardOffset). Only the shard's compressed bytes cross
+ * PCIe. Returns the decoded bytes of the shard; 0 on error or when the shard owns no block (hsr_last_error() is ""). */
+size_t hsr_decode_mt_shard(int stateCount, int bits, const uint8_t *pInData, size_t inLength, uint8_t *pOutData, size_t outCapacity,
+                           int shard, int shards, size_t *pShardOffset);
+
 int hsr_set_device(int device);
 
 /* Many independent streams of ONE codec in one launch. A raw or block_ stream is a single 32/64-lane recurrence

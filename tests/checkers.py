@@ -19,6 +19,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libhsrans_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libhsrans_ref.so")
+SYNTH_SO = os.path.join(ROOT, "oracle", "_build", "libhsr_synth.so")
 RAW, BLOCK, MT, RAW32BLK = 0, 1, 2, 3
 IMPL_SCALAR, IMPL_AVX2, IMPL_AVX512, IMPL_POOL = 0, 1, 2, 3
 
@@ -59,6 +60,25 @@ def oracle() -> C.CDLL:
         lib.hsro_mt_walk.argtypes = [u32, vp, sz, C.POINTER(OracleBlock), sz]
         _oracle = lib
     return _oracle
+
+
+_synth = None
+
+
+def synth_zipf(n: int, s: float = 1.0, seed: int = 42, segment_bytes: int = 0) -> np.ndarray:
+    """Deterministic Zipf(s) bytes from the generator built as a library of its own (oracle/Makefile): the same
+    source as the product's hsr_synth_zipf, without mapping the product library (bench.py --impl reference)."""
+    global _synth
+    if _synth is None:
+        if not os.path.exists(SYNTH_SO):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], stdout=subprocess.DEVNULL)
+        _synth = C.CDLL(SYNTH_SO)
+        _synth.hsr_synth_zipf.restype = C.c_int
+        _synth.hsr_synth_zipf.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_uint64, C.c_size_t]
+    out = np.empty(n, np.uint8)
+    if _synth.hsr_synth_zipf(out.ctypes.data, n, float(s), int(seed), int(segment_bytes)) != 0:
+        raise RuntimeError("hsr_synth_zipf failed")
+    return out
 
 
 def have_ref() -> bool:

@@ -1,0 +1,299 @@
+"""GPU (-m gpu), round 2: config 4 proper (reference-encoded 1 GB, sharded), overlapping launches, pooled host contexts,
+the encoder's own block table, the shard entry point, and the advisor's corruption cases. Everything goes through the
+C-ABI; nothing here reads /root/reference (streams come from oracle/_ref, which travels, or the golden fixtures)."""
+import ctypes
+import threading
+import time
+
+import numpy as np
+import pytest
+
+import checkers as ck
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(pkg):
+    if pkg.device_count() < 1:
+        pytest.fail("no CUDA device: the -m gpu tests must run on the B200 box")
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def config4(gpu):
+    """BASELINE config 4: 1,000,000,000-byte Zipf(1) pw64k stream, encoded by the reference's own mt_ 64x15 encoder."""
+    if not ck.have_ref():
+        pytest.skip("needs oracle/_ref (the reference encoder)")
+    data = ck.synth_zipf(1_000_000_000, 1.0, seed=42, segment_bytes=65536)
+    stream = ck.ref_encode(ck.MT, 64, 15, data)
+    return data, stream
+
+
+def test_config4_reference_encoded_1gb_two_shards(gpu, config4):
+    """The north-star config as worded: ONE reference-encoded 1 GB mt_64x15 stream, sharded by contiguous block range
+    through the shard API into one buffer — byte-equal to what the reference's own decoder makes of the stream."""
+    import torch
+    data, stream = config4
+    n = data.size
+    want_n, want = ck.ref_decode(ck.MT, 64, 15, stream, n, ck.IMPL_POOL)  # mt_rANS32x64_16w_decode_mt_15
+    assert want_n == n
+    out = torch.full((n + 64,), 0xCC, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    total, units = 0, 0
+    for r in range(2):
+        sh = gpu.PreparedStream.upload(ck.MT, 64, 15, stream, shard=r, shards=2)
+        assert sh.decode_async(out.data_ptr(), n, st) == 1
+        total += sh.shard_out_bytes
+        units += sh.units
+        torch.cuda.synchronize()
+        assert sh.status() == 0
+        sh.free()
+    got = out.cpu().numpy()
+    assert total == n and units > 15_000
+    assert np.array_equal(got[:n], want[:n]) and np.array_equal(got[:n], data) and np.all(got[n:] == 0xCC)
+
+
+def test_config4_host_entry_points_1gb(gpu, config4):
+    """hsr_decode, hsr_decode_mt_multi (2 shards on one device) and hsr_decode_mt_shard on the same 1 GB stream."""
+    data, stream = config4
+    n = data.size
+    hin, hout = gpu.host_alloc(stream.size), gpu.host_alloc(n)
+    hin.array[:] = stream
+    lib = gpu.lib()
+    hout.array[:] = 0xCC
+    assert lib.hsr_decode(ck.MT, 64, 15, hin.ptr, stream.size, hout.ptr, n) == n, gpu.last_error()
+    assert np.array_equal(hout.array, data)
+    hout.array[:] = 0xCC
+    devs = (ctypes.c_int * 3)(0, 0, 0)
+    assert lib.hsr_decode_mt_multi(64, 15, hin.ptr, stream.size, hout.ptr, n, devs, 3) == n, gpu.last_error()
+    assert np.array_equal(hout.array, data)
+    hout.array[:] = 0xCC
+    covered = 0
+    for r in range(4):
+        off = ctypes.c_size_t(0)
+        got = lib.hsr_decode_mt_shard(64, 15, hin.ptr, stream.size, hout.ptr, n, r, 4, ctypes.byref(off))
+        assert got > 0 and off.value == covered, (r, got, off.value, gpu.last_error())
+        covered += got
+    assert covered == n and np.array_equal(hout.array, data)
+    hin.free(); hout.free()
+
+
+def test_back_to_back_launches_overlap_and_stay_exact(gpu, golden):
+    """Consecutive units launches on one CUDA stream overlap (programmatic dependent launch, launch-private work slots):
+    many decodes of several prepared streams queued without a sync in between, then every output checked."""
+    import torch
+    st = torch.cuda.current_stream().cuda_stream
+    jobs = []
+    for name, fam, states, bits in (("multi", ck.MT, 64, 15), ("multi", ck.MT, 32, 12), ("multi", ck.RAW, 64, 12),
+                                    ("runs", ck.MT, 64, 11), ("small", ck.MT, 64, 10), ("runs", ck.MT, 32, 14)):
+        data = golden[f"in/{name}"]
+        ps = gpu.PreparedStream.upload(fam, states, bits, golden[f"stream/{name}/{fam}/{states}/{bits}"])
+        outs = [torch.full((data.size + 64,), 0xCC, dtype=torch.uint8, device="cuda") for _ in range(3)]
+        jobs.append((ps, data, outs))
+    for overlap in (1, 0, 1):
+        gpu.set_option("overlap", overlap)
+        for _, _, outs in jobs:
+            for o in outs:
+                o.fill_(0xCC)
+        for rep in range(40):          # 40 x 6 launches queued back to back
+            for ps, data, outs in jobs:
+                ps.decode_async(outs[rep % 3].data_ptr(), data.size, st)
+        torch.cuda.synchronize()
+        for ps, data, outs in jobs:
+            assert ps.status() == 0
+            for o in outs:
+                got = o.cpu().numpy()
+                assert np.array_equal(got[: data.size], data) and np.all(got[data.size:] == 0xCC)
+    # the same prepared stream from two CUDA streams at once (the advisor's shared-counter race): private work slots
+    ps, data, outs = jobs[0]
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for o in outs:
+        o.fill_(0xCC)
+    for rep in range(30):
+        ps.decode_async(outs[0].data_ptr(), data.size, s1.cuda_stream)
+        ps.decode_async(outs[1].data_ptr(), data.size, s2.cuda_stream)
+    torch.cuda.synchronize()
+    assert ps.status() == 0
+    for o in outs[:2]:
+        assert np.array_equal(o.cpu().numpy()[: data.size], data)
+    for ps, _, _ in jobs:
+        ps.free()
+    gpu.set_option("overlap", 1)
+
+
+def test_overlap_completion_is_in_stream_order(gpu):
+    """A short decode queued behind a long one must not report completion first: a D2H copy queued after both sees both."""
+    import torch
+    if not ck.have_ref():
+        pytest.skip("needs oracle/_ref")
+    long_data = ck.synth_zipf(40_000_000, 1.0, seed=9, segment_bytes=0)       # stationary: a few huge blocks, slow
+    short_data = ck.synth_zipf(300_000, 1.0, seed=10, segment_bytes=65536)
+    pl = gpu.PreparedStream.upload(ck.MT, 64, 15, ck.ref_encode(ck.MT, 64, 15, long_data))
+    psh = gpu.PreparedStream.upload(ck.MT, 64, 15, ck.ref_encode(ck.MT, 64, 15, short_data))
+    ol = torch.full((long_data.size,), 0xCC, dtype=torch.uint8, device="cuda")
+    osh = torch.full((short_data.size,), 0xCC, dtype=torch.uint8, device="cuda")
+    hl = torch.empty(long_data.size, dtype=torch.uint8).pin_memory()
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        ol.fill_(0xCC)
+        pl.decode_async(ol.data_ptr(), long_data.size, st)
+        psh.decode_async(osh.data_ptr(), short_data.size, st)
+        hl.copy_(ol, non_blocking=True)      # ordinary stream op behind both kernels
+        torch.cuda.synchronize()
+        assert np.array_equal(hl.numpy(), long_data) and np.array_equal(osh.cpu().numpy(), short_data)
+    pl.free(); psh.free()
+
+
+def test_concurrent_host_threads_overlap_on_one_device(gpu):
+    """K host threads decoding K streams lease K pooled contexts: their copies and kernels overlap, so the aggregate
+    beats the same calls made one after another (round 1 held one mutex per device for the whole call)."""
+    if not ck.have_ref():
+        pytest.skip("needs oracle/_ref")
+    k, n = 4, 100_000_000
+    lib = gpu.lib()
+    bufs = []
+    for i in range(k):
+        data = ck.synth_zipf(n, 1.0, seed=200 + i, segment_bytes=65536)
+        stream = ck.ref_encode(ck.MT, 64, 15, data)
+        hin, hout = gpu.host_alloc(stream.size), gpu.host_alloc(n)
+        hin.array[:] = stream
+        bufs.append((data, stream.size, hin, hout))
+
+    def one(i):
+        data, comp, hin, hout = bufs[i]
+        assert lib.hsr_decode(ck.MT, 64, 15, hin.ptr, comp, hout.ptr, n) == n
+
+    for i in range(k):
+        one(i)                           # warm-up: contexts, scratch
+    threads = [threading.Thread(target=one, args=(i,)) for i in range(k)]
+    for t in threads: t.start()
+    for t in threads: t.join()           # warm-up of the pooled contexts
+
+    def serial():
+        t0 = time.perf_counter()
+        for _ in range(3):
+            for i in range(k):
+                one(i)
+        return time.perf_counter() - t0
+
+    def parallel():
+        t0 = time.perf_counter()
+        for _ in range(3):
+            threads = [threading.Thread(target=one, args=(i,)) for i in range(k)]
+            for t in threads: t.start()
+            for t in threads: t.join()
+        return time.perf_counter() - t0
+
+    t_serial = min(serial(), serial())
+    for _, _, _, hout in bufs:
+        hout.array[:] = 0xCC
+    t_parallel = min(parallel(), parallel())
+    for data, _, _, hout in bufs:
+        assert np.array_equal(hout.array, data)
+    print(f"\n4 x 100 MB mt_64x15 host decodes: serial {t_serial * 1e3:.1f} ms, 4 threads {t_parallel * 1e3:.1f} ms, "
+          f"ratio {t_serial / t_parallel:.2f}")
+    # One call already overlaps its own H2D, kernels and D2H; what the pool adds is the fill and drain of each call's
+    # pipeline hidden behind its neighbours'. PCIe bounds the rest (both directions busy in either mode).
+    assert t_parallel < t_serial / 1.15, (t_serial, t_parallel)
+    for _, _, hin, hout in bufs:
+        hin.free(); hout.free()
+
+
+def test_encoder_block_table_skips_the_chain_walk(gpu):
+    import torch
+    st = torch.cuda.current_stream().cuda_stream
+    for n, states, bits, policy in ((30_000_019, 64, 15, False), (30_000_019, 32, 12, False), (20_000_000, 64, 13, True), (64 * 1000 + 7, 32, 10, False)):
+        data = ck.synth_zipf(n, 1.0, seed=n % 97, segment_bytes=65536)
+        if policy:
+            data[3_000_000:5_000_000] = 0x41     # a run of one byte: run blocks in the table
+        d_in = torch.from_numpy(data).cuda()
+        bound = gpu.encode_mt_bound(states, n)
+        d_out = torch.empty(bound, dtype=torch.uint8, device="cuda")
+        cap = gpu.encode_mt_index_bound(states, n)
+        d_idx = torch.zeros(cap * 48, dtype=torch.uint8, device="cuda")
+        comp, units = gpu.encode_mt_device_indexed(states, bits, d_in.data_ptr(), n, d_out.data_ptr(), bound, d_idx.data_ptr(), cap, 0, policy, st)
+        assert comp > 0 and 0 < units <= cap
+        ps = gpu.PreparedStream.from_device_indexed(states, bits, d_out.data_ptr(), comp, d_idx.data_ptr(), units)
+        # the table is what the chain walk finds (run blocks are cut into 4 MiB fills by the walk only)
+        walked = gpu.PreparedStream.from_device(ck.MT, states, bits, d_out.data_ptr(), comp)
+        a = [(b.inOffset, b.inEnd, b.outOffset, b.count, b.kind, b.symbol, b.tail) for b in ps.index() if b.kind == 0]
+        b_ = [(b.inOffset, b.inEnd, b.outOffset, b.count, b.kind, b.symbol, b.tail) for b in walked.index() if b.kind == 0]
+        assert a == b_
+        out = torch.full((n + 64,), 0xCC, dtype=torch.uint8, device="cuda")
+        ps.decode_async(out.data_ptr(), n, st)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        assert ps.status() == 0 and np.array_equal(got[:n], data) and np.all(got[n:] == 0xCC)
+        # a table that lies is refused, never trusted
+        idx = d_idx.clone()
+        rec = idx[:48].cpu().numpy().copy()
+        rec[8:16] = np.frombuffer(np.uint64(comp + 4096).tobytes(), np.uint8)      # inEnd past the stream
+        idx[:48] = torch.from_numpy(rec).cuda()
+        with pytest.raises(gpu.HsrError):
+            gpu.PreparedStream.from_device_indexed(states, bits, d_out.data_ptr(), comp, idx.data_ptr(), units)
+        ps.free(); walked.free()
+
+
+def test_corrupted_32blk_headers_never_fault(gpu, golden_rank4):
+    """Advisor, round 1: an odd sub-stream size in a RAW32BLK header made every later read head odd — a sticky
+    misaligned-address fault on the GPU. Flip bits all over the header of 32blk (and 16-state) streams."""
+    rng = np.random.default_rng(777)
+    keys = [k for k in golden_rank4 if k.startswith("stream/")]
+    picked = [k for k in keys if "/3/" in k][:6] + [k for k in keys if "/0/16/" in k][:3]
+    assert picked
+    for key in picked:
+        _, name, fam, states, bits = key.split("/")
+        fam, states, bits = int(fam), int(states), int(bits)
+        good = golden_rank4[key]
+        data = golden_rank4[f"in/{name}"]
+        n = data.size
+        if n < states:
+            continue
+        sizes_at = 16 + 512 + 4 * 32
+        for trial in range(16):
+            bad = good.copy()
+            if fam == 3 and trial < 8:   # the size table itself: low bits first
+                pos = sizes_at + 4 * int(rng.integers(0, 31)) + int(rng.integers(0, 2))
+                bad[pos] ^= np.uint8(1 << int(rng.integers(0, 3)))
+            else:
+                for _ in range(int(rng.integers(1, 5))):
+                    pos = int(rng.integers(0, min(bad.size, 1024)))
+                    bad[pos] ^= np.uint8(1 << int(rng.integers(0, 8)))
+            out = np.full(n + 256, 0xCC, np.uint8)
+            got, _ = gpu.decode(fam, states, bits, bad, n, out=out)
+            assert got <= n and np.all(out[n:] == 0xCC)
+        n_ok, out = gpu.decode(fam, states, bits, good, n)       # the device is still healthy
+        want_n, want = ck.oracle_decode(fam, states, bits, good, n)
+        assert n_ok == want_n and np.array_equal(out[:n_ok], want[:n_ok]), key
+
+
+def test_batch_argument_edges(gpu, golden):
+    """Advisor, round 1: odd stream offsets must not reach the kernels; decodedLengths is written on every return."""
+    data = golden["in/multi"]
+    stream = golden["stream/multi/0/64/12"]
+    in_base = np.zeros(1 + stream.size + 64, np.uint8)
+    in_base[1: 1 + stream.size] = stream                       # stream at an ODD offset
+    out_base = np.full(data.size + 64, 0xCC, np.uint8)
+    ok, lengths = gpu.decode_batch(ck.RAW, 64, 12, in_base, out_base, [(1, stream.size, 0, data.size)])
+    assert ok == 0 and lengths[0] == 0 and np.all(out_base == 0xCC)
+    # all streams malformed: lengths are zeroed, not left as found
+    junk = np.zeros(4096, np.uint8)
+    arr = (gpu.capi.BatchItem * 2)(gpu.capi.BatchItem(0, 2048, 0, 100), gpu.capi.BatchItem(2048, 2048, 128, 100))
+    lens = np.full(2, 0xDEADBEEF, np.uint64)
+    got = gpu.lib().hsr_decode_batch(ck.RAW, 64, 12, junk.ctypes.data, out_base.ctypes.data, arr, 2, lens.ctypes.data)
+    assert got == 0 and lens[0] == 0 and lens[1] == 0
+    # an even offset still works
+    in2 = np.zeros(2 + stream.size + 64, np.uint8)
+    in2[2: 2 + stream.size] = stream
+    ok, lengths = gpu.decode_batch(ck.RAW, 64, 12, in2, out_base, [(2, stream.size, 0, data.size)])
+    assert ok == 1 and lengths[0] == data.size and np.array_equal(out_base[: data.size], data)
+
+
+def test_hostile_header_lengths_are_refused(gpu, golden):
+    stream = golden["stream/runs/2/64/11"].copy()
+    stream[:8] = np.frombuffer(np.uint64(1 << 50).tobytes(), np.uint8)      # decoded length: 1 PiB
+    with pytest.raises(gpu.HsrError):
+        gpu.PreparedStream.upload(ck.MT, 64, 11, stream)
+    with pytest.raises(gpu.HsrError):
+        gpu.mt_index(64, stream)
