@@ -31,6 +31,7 @@ never maps the product library.
 from __future__ import annotations
 
 import argparse
+import faulthandler
 import json
 import os
 import sys
@@ -45,6 +46,17 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 FAMILY_RAW, FAMILY_BLOCK, FAMILY_MT, FAMILY_RAW32BLK = 0, 1, 2, 3
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+faulthandler.enable()  # a native abort still leaves the Python stack on stderr
+
+
+def _stage(msg):
+    if os.environ.get("HSR_BENCH_TRACE"):
+        print(f"[bench +{time.time() - _T0:7.2f}s] {msg}", file=sys.stderr, flush=True)
+
+
+_T0 = time.time()
 
 
 def parse_args():
@@ -443,8 +455,10 @@ def main():
     pkg.set_option("overlap", 0 if a.no_overlap else 1)
 
     # ---------------------------------------------------------------- the ONE stream: same bytes on every rank, encoded once
+    _stage('synth')
     data = make_data(a)
     n = data.size
+    _stage('reference encode')
     t0 = time.time()
     if rank == 0:
         stream = ref_encode(a, data)
@@ -460,7 +474,9 @@ def main():
     comp = stream.size
 
     # ---------------------------------------------------------------- kernel path: this rank's shard + index resident in HBM
+    _stage('upload')
     ps = pkg.PreparedStream.upload(FAMILY_MT, a.states, a.bits, stream, shard=rank, shards=world)
+    _stage('first decode + check')
     units = int(ps.units)
     my_off, my_bytes, my_in = int(ps.shard_out_offset), int(ps.shard_out_bytes), int(ps.shard_in_bytes)
     out_dev = torch.empty(my_bytes + 256, dtype=torch.uint8, device="cuda")
@@ -493,6 +509,7 @@ def main():
         del full
         gathered = meta
 
+    _stage('warmup + timed steps')
     for _ in range(a.warmup):
         ps.decode_async(out_dev.data_ptr(), my_bytes, cur, True)
     barrier()
@@ -517,6 +534,7 @@ def main():
     clocks = clk.summary()
     clocks["window"] = "timed steps" if (a.kernel_only or a.headline_only) else "timed steps + 0.25 s of the same launches (untimed)"
 
+    _stage('serialised steps')
     # the same K steps strictly serialised (one launch at a time, an event after each): per-launch durations
     pkg.set_option("overlap", 0)
     barrier()
@@ -542,6 +560,7 @@ def main():
         return
 
     # ---------------------------------------------------------------- end to end through the drop-in host call
+    _stage('e2e')
     e2e_steps = a.e2e_steps or min(a.steps, 10)
     lib = pkg.lib()
     e2e = None
@@ -627,6 +646,7 @@ def main():
 
     if rank == 0:
         # ---------------------------------------------------------------- index timings (reported apart, SURVEY §8d "I")
+        _stage('index timings')
         index_host_ms = ps.index_ms
         dev_in = torch.from_numpy(stream).cuda()
         ds = pkg.PreparedStream.from_device(FAMILY_MT, a.states, a.bits, dev_in.data_ptr(), comp)
@@ -683,8 +703,10 @@ def main():
             line["e2e_one_process_per_gpu"] = e2e_shards
         if weak:
             line["weak_scaling"] = weak
+        _stage('cpu baseline')
         if not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a, stream, n)
+        _stage('other configs')
         if not a.headline_only:
             line["other_configs"] = other_configs(pkg, torch, a, peak, a.extra)
         print(json.dumps(line), flush=True)

@@ -32,7 +32,7 @@ __device__ __forceinline__ bool next_unit(const DecodeParams &p, uint32_t lane, 
   uint32_t b = 0;
   if (lane == 0)
     b = atomicAdd(p.work, 1u);
-  b = __shfl_sync(kFull, b, 0);
+  b = __reduce_add_sync(kFull, b); // lane 0's claim in a uniform register: a provably warp-uniform loop exit (see units_kernel_body)
   if (b >= p.numBlocks)
     return false;
   const hsr_block_t *blk = p.blocks + b;

@@ -111,9 +111,11 @@ size_t hsref_encode_raw_with_hist(int N, int bits, const uint8_t *in, size_t n, 
 
 int hsref_pool_threads(void) { return (int)g_pool_threads; }
 
+void hsref_pool_destroy(void);
+
 int hsref_pool_create(int threads) // threads <= 0: hardware_concurrency() - 1 like src/main.cpp:167
 {
-  if (g_pool) thread_pool_destroy(&g_pool);
+  hsref_pool_destroy();
   size_t t = threads > 0 ? (size_t)threads : thread_pool_max_threads();
   if (threads <= 0) t = t > 1 ? t - 1 : 1;
   g_pool = thread_pool_new(t);
@@ -123,7 +125,8 @@ int hsref_pool_create(int threads) // threads <= 0: hardware_concurrency() - 1 l
 
 void hsref_pool_destroy(void)
 {
-  if (g_pool) thread_pool_destroy(&g_pool);
+  if (g_pool) thread_pool_destroy(&g_pool); // deletes the pool but leaves the caller's pointer as it was (src/thread_pool.cpp:108-114)
+  g_pool = nullptr;
   g_pool_threads = 0;
 }
 
