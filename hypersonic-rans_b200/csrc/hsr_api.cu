@@ -1013,44 +1013,101 @@ struct InFlight {
 
 static bool start_h2d(DeviceCtx *c, const uint8_t *in, uint64_t lo, uint64_t hi, InFlight *fl)
 {
+  // pieces grow 2, 2, 4, 8, 16, 16, ... MiB: the first decode launch waits for 2 MiB instead of 16 (0.04 ms instead of
+  // 0.3 ms of DMA), so the device -> host stream — the longer of the two directions — starts that much earlier
   const long optMb = g_optChunkMb;
-  const uint64_t piece = (optMb > 0 ? (uint64_t)optMb : 16ull) << 20;
+  const uint64_t fixedPiece = optMb > 0 ? (uint64_t)optMb << 20 : 0;
   fl->lo = lo;
   fl->ends.clear();
   if (!grow(c->dIn, c->inCap, (size_t)(hi - lo) + 16)) return false;
-  const size_t pieces = (size_t)((hi - lo + piece - 1) / piece);
-  if (!ensure_events(c, pieces)) return false;
-  for (size_t k = 0; k < pieces; k++) {
-    const uint64_t a = lo + k * piece, b = std::min(hi, a + piece);
+  uint64_t a = lo;
+  for (size_t k = 0; a < hi; k++) {
+    const uint64_t piece = fixedPiece ? fixedPiece : std::min<uint64_t>(16ull << 20, (2ull << 20) << (k > 0 ? k - 1 : 0));
+    const uint64_t b = std::min(hi, a + piece);
+    if (!ensure_events(c, k + 1)) return false;
     CU_TRY(cudaMemcpyAsync(c->dIn + (a - lo), in + a, (size_t)(b - a), cudaMemcpyHostToDevice, c->sIn), return false);
     CU_TRY(cudaEventRecord(c->evIn[k], c->sIn), return false);
     fl->ends.push_back(b);
+    a = b;
   }
   return true;
 }
 
-// Decodes units [first, last) whose compressed bytes are arriving through `fl`: contiguous unit ranges are
-// launched as soon as the copy piece holding their last byte has landed, and each range's decoded bytes go back
-// to the host while later ranges are still decoding (three streams: copy-in, run, copy-out).
+// Decodes contiguous unit ranges whose compressed bytes are arriving through an InFlight copy: a range is launched as
+// soon as the copy piece holding its last byte has landed, and its decoded bytes go back to the host while later
+// ranges are still decoding (three streams: copy-in, run, copy-out). Ranges can be handed over while the header chain
+// is still being walked (launch() from inside the walk), so the first decoded bytes leave the device after ~0.1 ms
+// instead of after the whole 1.7 ms-per-GB walk; range sizes grow 6, 12, 24, 48, 48, ... MiB of traffic for the same
+// reason.
+struct UnitPipeline {
+  DeviceCtx *c = nullptr;
+  int family = 0, N = 0, bits = 0;
+  uint8_t *out = nullptr;
+  uint64_t outLo = 0;
+  const InFlight *fl = nullptr;
+  size_t piece = 0, ranges = 0;
+
+  static uint64_t range_bytes(size_t r) { return std::min<uint64_t>(48ull << 20, (6ull << 20) << std::min<size_t>(r, 8)); }
+  uint64_t next_range_bytes() const { return range_bytes(ranges); }
+
+  // decoded bytes [outLo_, outLo_ + outBytes) of the stream will be produced
+  bool begin(DeviceCtx *ctx, int family_, int N_, int bits_, uint8_t *out_, uint64_t outLo_, uint64_t outBytes, const InFlight *fl_)
+  {
+    c = ctx; family = family_; N = N_; bits = bits_; out = out_; outLo = outLo_; fl = fl_;
+    piece = 0; ranges = 0;
+    if (!grow(c->dOut, c->outCap, (size_t)outBytes + 16)) return false;
+    if (!grow(c->dCounters, c->countersCap, 4)) return false;
+    CU_TRY(cudaMemsetAsync(c->dCounters, 0, 16, c->sRun), return false); // [1]: status bits, OR over every range
+    return true;
+  }
+
+  // units[0 .. count): device-visible (mapped host memory), consecutive in the stream
+  bool launch(const hsr_block_t *units, size_t count)
+  {
+    if (count == 0) return true;
+    while (c->evRun.size() <= ranges) {
+      cudaEvent_t e;
+      CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), return false);
+      c->evRun.push_back(e);
+    }
+    const uint64_t needEnd = units[count - 1].inEnd;
+    while (piece + 1 < fl->ends.size() && fl->ends[piece] < needEnd) piece++;
+    CU_TRY(cudaStreamWaitEvent(c->sRun, c->evIn[piece], 0), return false);
+    uint64_t rangeDecoded = 0;
+    for (size_t k = 0; k < count; k++) rangeDecoded += units[k].count;
+    if (launch_units(family, N, bits, c->dIn, fl->lo, c->dOut, outLo, units, (uint32_t)count, c->dCounters + 1, c->sRun, nullptr, rangeDecoded) < 0)
+      return false;
+    CU_TRY(cudaEventRecord(c->evRun[ranges], c->sRun), return false);
+    CU_TRY(cudaStreamWaitEvent(c->sOut, c->evRun[ranges], 0), return false);
+    const uint64_t oLo = units[0].outOffset, oHi = units[count - 1].outOffset + units[count - 1].count;
+    CU_TRY(cudaMemcpyAsync(out + oLo, c->dOut + (oLo - outLo), (size_t)(oHi - oLo), cudaMemcpyDeviceToHost, c->sOut), return false);
+    ranges++;
+    return true;
+  }
+
+  // waits for everything issued so far; false if a copy failed or a decoded unit was malformed
+  bool finish()
+  {
+    uint32_t status[4] = {0, 0, 0, 0};
+    bool ok = true;
+    // the status word is read on the copy-out stream, which has waited for every launch
+    if (cudaMemcpyAsync(status, c->dCounters, 16, cudaMemcpyDeviceToHost, c->sOut) != cudaSuccess) ok = false;
+    if (cudaStreamSynchronize(c->sOut) != cudaSuccess) ok = false;
+    if (cudaStreamSynchronize(c->sIn) != cudaSuccess) ok = false;
+    if (cudaStreamSynchronize(c->sRun) != cudaSuccess) ok = false;
+    if (!ok) { set_err("CUDA stream failed: %s", cudaGetErrorString(cudaGetLastError())); return false; }
+    if (status[1]) { set_err("malformed stream (device status 0x%x)", status[1]); return false; }
+    return true;
+  }
+};
+
+// units [first, last) of a complete index, compressed bytes arriving through `fl`
 static bool run_units_pipelined(DeviceCtx *c, int family, int N, int bits, uint8_t *out, const hsr_block_t *units, size_t first,
                                 size_t last, const InFlight &fl)
 {
   if (first >= last) return true;
   const uint64_t outLo = units[first].outOffset, outHi = units[last - 1].outOffset + units[last - 1].count;
   const size_t count = last - first;
-
-  const uint64_t rangeBytes = 48ull << 20; // compressed + decoded traffic per launch
-  std::vector<size_t> cuts{first};
-  uint64_t acc = 0;
-  for (size_t k = first; k < last; k++) {
-    acc += (units[k].inEnd - units[k].inOffset) + units[k].count;
-    if (acc >= rangeBytes && k + 1 < last) { cuts.push_back(k + 1); acc = 0; }
-  }
-  cuts.push_back(last);
-  const size_t nRanges = cuts.size() - 1;
-
-  if (!grow(c->dOut, c->outCap, (size_t)(outHi - outLo) + 16)) return false;
-  if (!grow(c->dCounters, c->countersCap, 4)) return false;
   const hsr_block_t *devBlocks = nullptr; // device-visible address of units[first]
   if (units >= c->hBlocks && units + last <= c->hBlocks + c->hBlocksCap) {
     devBlocks = units + first; // already in the mapped buffer (UVA: same address on the device)
@@ -1059,37 +1116,20 @@ static bool run_units_pipelined(DeviceCtx *c, int family, int N, int bits, uint8
     memcpy(c->hBlocks, units + first, count * sizeof(hsr_block_t));
     devBlocks = c->hBlocks;
   }
-  while (c->evRun.size() < nRanges) {
-    cudaEvent_t e;
-    CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), return false);
-    c->evRun.push_back(e);
+  UnitPipeline pipe;
+  if (!pipe.begin(c, family, N, bits, out, outLo, outHi - outLo, &fl)) return false;
+  size_t a = 0;
+  uint64_t acc = 0;
+  for (size_t k = 0; k < count; k++) {
+    acc += (devBlocks[k].inEnd - devBlocks[k].inOffset) + devBlocks[k].count;
+    if (acc >= pipe.next_range_bytes() && k + 1 < count) {
+      if (!pipe.launch(devBlocks + a, k + 1 - a)) { pipe.finish(); return false; }
+      a = k + 1;
+      acc = 0;
+    }
   }
-
-  CU_TRY(cudaMemsetAsync(c->dCounters, 0, 16, c->sRun), return false); // [1]: status bits, OR over every range
-
-  size_t piece = 0;
-  for (size_t r = 0; r < nRanges; r++) {
-    const size_t a = cuts[r], b = cuts[r + 1];
-    const uint64_t needEnd = units[b - 1].inEnd;
-    while (piece + 1 < fl.ends.size() && fl.ends[piece] < needEnd) piece++;
-    CU_TRY(cudaStreamWaitEvent(c->sRun, c->evIn[piece], 0), return false);
-    uint64_t rangeDecoded = 0;
-    for (size_t k = a; k < b; k++) rangeDecoded += units[k].count;
-    if (launch_units(family, N, bits, c->dIn, fl.lo, c->dOut, outLo, devBlocks + (a - first), (uint32_t)(b - a), c->dCounters + 1, c->sRun,
-                     nullptr, rangeDecoded) < 0)
-      return false;
-    CU_TRY(cudaEventRecord(c->evRun[r], c->sRun), return false);
-    CU_TRY(cudaStreamWaitEvent(c->sOut, c->evRun[r], 0), return false);
-    const uint64_t oLo = units[a].outOffset, oHi = units[b - 1].outOffset + units[b - 1].count;
-    CU_TRY(cudaMemcpyAsync(out + oLo, c->dOut + (oLo - outLo), (size_t)(oHi - oLo), cudaMemcpyDeviceToHost, c->sOut), return false);
-  }
-  uint32_t status[4] = {0, 0, 0, 0};
-  CU_TRY(cudaMemcpyAsync(status, c->dCounters, 16, cudaMemcpyDeviceToHost, c->sOut), return false);
-  CU_TRY(cudaStreamSynchronize(c->sOut), return false);
-  CU_TRY(cudaStreamSynchronize(c->sIn), return false);
-  CU_TRY(cudaStreamSynchronize(c->sRun), return false);
-  if (status[1]) { set_err("malformed stream (device status 0x%x)", status[1]); return false; }
-  return true;
+  const bool launched = pipe.launch(devBlocks + a, count - a);
+  return pipe.finish() && launched;
 }
 
 // units [first, last) of an already indexed stream, from host memory, on `device`
@@ -1144,23 +1184,44 @@ static size_t decode_impl(int family, int N, int bits, const uint8_t *in, size_t
     const hsr_block_t u = raw_unit(family, N, h);
     return decode_units_from_host(device, family, N, bits, in, out, &u, 0, 1) ? (size_t)h.n : 0;
   }
-  // mt_: start moving the whole stream to the device, walk the header chain on the host meanwhile
+  // mt_: start moving the whole stream to the device and walk the header chain on the host meanwhile; every range of
+  // units is launched from inside the walk, as soon as the walk has passed it
   CtxLease lease(device);
   DeviceCtx *c = lease.get();
   if (!c) return 0;
   InFlight fl;
   if (!start_h2d(c, in, 0, h.compLen, &fl)) return 0;
-  if (!grow_host_blocks(c, (size_t)std::max<uint64_t>(64, h.n / 32768 + 64))) return 0;
-  long cnt = hsr_mt_index(N, in, (size_t)h.compLen, c->hBlocks, c->hBlocksCap);
-  if (cnt > (long)c->hBlocksCap) {
+  if (!grow_host_blocks(c, (size_t)std::max<uint64_t>(64, h.n / 32768 + 64))) { cudaStreamSynchronize(c->sIn); return 0; }
+  UnitPipeline pipe;
+  if (!pipe.begin(c, family, N, bits, out, 0, h.n, &fl)) { cudaStreamSynchronize(c->sIn); return 0; }
+  size_t launched = 0, have = 0;
+  uint64_t acc = 0;
+  bool overflow = false, failed = false;
+  std::string launchErr;
+  const long cnt = mt_walk(N, in, (size_t)h.compLen, [&](const hsr_block_t &b, size_t at) {
+    if (overflow || failed) return;
+    if (at >= c->hBlocksCap) { overflow = true; return; } // more units than the estimate: finished below, after a re-walk
+    c->hBlocks[at] = b;
+    have = at + 1;
+    acc += (b.inEnd - b.inOffset) + b.count;
+    if (acc >= pipe.next_range_bytes()) {
+      if (!pipe.launch(c->hBlocks + launched, have - launched)) { failed = true; launchErr = g_err; }
+      launched = have;
+      acc = 0;
+    }
+  }, nullptr);
+  if (cnt >= 0 && !failed && !overflow && !pipe.launch(c->hBlocks + launched, have - launched)) { failed = true; launchErr = g_err; }
+  const std::string walkErr = g_err;
+  const bool drained = pipe.finish();
+  if (cnt < 0) { g_err = walkErr; return 0; } // ranges already decoded wrote only bytes of well-formed blocks; the call still fails
+  if (failed) { g_err = launchErr; return 0; }
+  if (!drained) return 0;
+  if (overflow) { // rare: tiny blocks / long fills. The compressed bytes are all on the device by now.
     if (!grow_host_blocks(c, (size_t)cnt)) return 0;
-    cnt = hsr_mt_index(N, in, (size_t)h.compLen, c->hBlocks, c->hBlocksCap);
+    if (hsr_mt_index(N, in, (size_t)h.compLen, c->hBlocks, c->hBlocksCap) != cnt) return 0;
+    if (!run_units_pipelined(c, family, N, bits, out, c->hBlocks, launched, (size_t)cnt, fl)) return 0;
   }
-  if (cnt < 0) {
-    cudaStreamSynchronize(c->sIn);
-    return 0;
-  }
-  return run_units_pipelined(c, family, N, bits, out, c->hBlocks, 0, (size_t)cnt, fl) ? (size_t)h.n : 0;
+  return (size_t)h.n;
 }
 
 extern "C" size_t hsr_decode(int family, int N, int bits, const uint8_t *in, size_t inLength, uint8_t *out, size_t outCapacity)

@@ -9,7 +9,8 @@
 // byte-identical to the reference encoder's output.
 //
 // Pipeline (all on one CUDA stream):
-//   enc_hist_kernel      one CTA per block: shared-memory-atomic byte counts + the reference's normalize_hist
+//   seg_count_kernel     one CTA per block: byte counts in conflict-free shared-memory counter columns (hsr_hist.cu)
+//   seg_normalize_kernel the reference's normalize_hist, one LANE per block (hsr_hist_device.cuh)
 //   enc_block_kernel     one warp per block, one rANS state per lane (two for N = 64): walks the block BACKWARDS
 //                        (src/block_codec64.h:55-100), renormalisation words handed out by ballot/popc in reverse,
 //                        written downward into a per-block scratch slot; x / freq by exact reciprocal multiply
@@ -62,20 +63,11 @@ __device__ __forceinline__ uint64_t slot_end(const EncPlan &pl, uint32_t k)
 
 // ---------------------------------------------------------------------------------------------- per-block histograms
 
-constexpr int kSegWarps = 4; // warps per CTA in the per-block histogram kernels
+// per-block histograms: raw counts by one CTA per block, normalisation by one lane per block (hsr_hist.cu)
+bool launch_range_histograms(const uint8_t *dData, const SegPlan &pl, int bits, uint32_t *dCounts32, uint16_t *dCounts, cudaStream_t st);
+bool launch_range_counts(const uint8_t *dData, const SegPlan &pl, uint32_t *dCounts32, cudaStream_t st);
 
-__global__ void __launch_bounds__(kSegWarps * 32) enc_hist_kernel(const uint8_t *data, EncPlan pl, int bits, uint16_t *counts)
-{
-  __shared__ uint32_t sHist[kSegWarps][256];
-  __shared__ uint16_t sCapped[kSegWarps][256];
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  for (uint32_t k = blockIdx.x * kSegWarps + warp; k < pl.numBlocks; k += gridDim.x * kSegWarps) {
-    if (block_is_run(pl, k)) continue;
-    const uint64_t begin = block_begin(pl, k), end = block_end(pl, k);
-    warp_observe(data, begin, end, sHist[warp], lane);
-    warp_normalize(sHist[warp], end - begin, bits, sCapped[warp], sHist[warp], counts + (uint64_t)k * 256, lane); // :209-210
-  }
-}
+static SegPlan seg_plan(const EncPlan &pl) { return SegPlan{pl.starts, pl.kinds, pl.blockSize, pl.n, pl.numBlocks}; }
 
 // ---------------------------------------------------------------------------------------------- block encoder
 
@@ -329,18 +321,6 @@ __global__ void __launch_bounds__(256, 8) enc_assemble_kernel(EncPlan pl, const 
 // instead of a second, normalised histogram per candidate, and runs are found at segment granularity.
 constexpr uint32_t kSegBytes = 65536; // MinBlockSize for every bit width (:34-45)
 
-__global__ void __launch_bounds__(kSegWarps * 32) enc_seg_count_kernel(const uint8_t *data, uint64_t n, uint32_t numSegs, uint32_t *segCounts)
-{
-  __shared__ uint32_t sHist[kSegWarps][256];
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  for (uint32_t t = blockIdx.x * kSegWarps + warp; t < numSegs; t += gridDim.x * kSegWarps) {
-    const uint64_t begin = (uint64_t)t * kSegBytes, end = t + 1 == numSegs ? n : begin + kSegBytes;
-    warp_observe(data, begin, end, sHist[warp], lane);
-    for (int i = lane; i < 256; i += 32) segCounts[(uint64_t)t * 256 + i] = sHist[warp][i];
-    __syncwarp();
-  }
-}
-
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll
@@ -506,6 +486,7 @@ bool make_plan(int N, uint64_t n, size_t blockSize, EncPlan *pl)
 struct EncScratch {
   int device = -1;
   uint16_t *dCounts = nullptr;
+  uint32_t *dCounts32 = nullptr; // raw per-block byte counts between the count and normalise kernels
   uint8_t *dScratch = nullptr;
   EncBlockMeta *dMeta = nullptr;
   uint64_t *dOffsets = nullptr;
@@ -535,10 +516,10 @@ struct EncScratch {
   bool ensure(size_t blocks, size_t scratchBytes)
   {
     if (blocks > blocksCap) {
-      cudaFree(dCounts); cudaFree(dMeta); cudaFree(dOffsets);
-      dCounts = nullptr; dMeta = nullptr; dOffsets = nullptr; blocksCap = 0;
+      cudaFree(dCounts); cudaFree(dCounts32); cudaFree(dMeta); cudaFree(dOffsets);
+      dCounts = nullptr; dCounts32 = nullptr; dMeta = nullptr; dOffsets = nullptr; blocksCap = 0;
       const size_t want = blocks + blocks / 8 + 16;
-      if (cudaMalloc(&dCounts, want * 512) != cudaSuccess || cudaMalloc(&dMeta, want * sizeof(EncBlockMeta)) != cudaSuccess ||
+      if (cudaMalloc(&dCounts, want * 512) != cudaSuccess || cudaMalloc(&dCounts32, want * 1024) != cudaSuccess || cudaMalloc(&dMeta, want * sizeof(EncBlockMeta)) != cudaSuccess ||
           cudaMalloc(&dOffsets, (want + 1) * 8) != cudaSuccess)
         return false;
       blocksCap = want;
@@ -601,8 +582,7 @@ static size_t encode_fixed_device(int N, int bits, const void *dInV, size_t leng
   }
   cudaMemsetAsync(sc.dCounter, 0, 16, st);
   const unsigned gridH = (unsigned)std::min<uint64_t>(pl.numBlocks, (uint64_t)sms * 8);
-  const unsigned gridS = (unsigned)std::min<uint64_t>((pl.numBlocks + kSegWarps - 1) / kSegWarps, (uint64_t)sms * 16);
-  enc_hist_kernel<<<gridS, kSegWarps * 32, 0, st>>>(dIn, pl, bits, sc.dCounts);
+  if (!launch_range_histograms(dIn, seg_plan(pl), bits, sc.dCounts32, sc.dCounts, st)) return 0;
   const unsigned gridE = (unsigned)std::min<uint64_t>(pl.numBlocks, (uint64_t)sms * 32);
   if (N == 32) launch_encode_n<32>(bits, dIn, pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dCounter, gridE, st);
   else launch_encode_n<64>(bits, dIn, pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dCounter, gridE, st);
@@ -654,8 +634,7 @@ static size_t encode_policy_device(int N, int bits, const void *dInV, size_t len
   }
   const uint32_t headerBytes = 16 + 4 * (uint32_t)N + 512;
   cudaMemsetAsync(sc.dCounter, 0, 16, st);
-  const unsigned gridS = (unsigned)std::min<uint64_t>((numSegs + kSegWarps - 1) / kSegWarps, (uint64_t)sms * 16);
-  enc_seg_count_kernel<<<gridS, kSegWarps * 32, 0, st>>>(dIn, length, numSegs, sc.dSegCounts);
+  if (!launch_range_counts(dIn, SegPlan{nullptr, nullptr, (uint64_t)kSegBytes, (uint64_t)length, numSegs}, sc.dSegCounts, st)) return 0;
   const uint32_t chunks = (numSegs + segsPerChunk - 1) / segsPerChunk;
   enc_policy_kernel<<<std::min<uint32_t>(chunks, (uint32_t)sms * 32u), 32, 0, st>>>(sc.dSegCounts, length, numSegs, segsPerChunk, bits, headerBytes, sc.dFlags);
   enc_blocks_kernel<<<1, 1024, 0, st>>>(sc.dFlags, numSegs, length, sc.dStarts, sc.dKinds, sc.dResult);
@@ -671,8 +650,7 @@ static size_t encode_policy_device(int N, int bits, const void *dInV, size_t len
   pl.n = length; pl.blockSize = 0; pl.numBlocks = numBlocks; pl.lastStart = 0; pl.slotBytes = 0;
   pl.starts = sc.dStarts; pl.kinds = sc.dKinds; pl.slotPad = slotPad;
   const unsigned gridH = (unsigned)std::min<uint64_t>(numBlocks, (uint64_t)sms * 8);
-  const unsigned gridB = (unsigned)std::min<uint64_t>((numBlocks + kSegWarps - 1) / kSegWarps, (uint64_t)sms * 16);
-  enc_hist_kernel<<<gridB, kSegWarps * 32, 0, st>>>(dIn, pl, bits, sc.dCounts);
+  if (!launch_range_histograms(dIn, seg_plan(pl), bits, sc.dCounts32, sc.dCounts, st)) return 0;
   const unsigned gridE = (unsigned)std::min<uint64_t>(numBlocks, (uint64_t)sms * 32);
   if (N == 32) launch_encode_n<32>(bits, dIn, pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dCounter, gridE, st);
   else launch_encode_n<64>(bits, dIn, pl, sc.dCounts, sc.dScratch, sc.dMeta, sc.dCounter, gridE, st);

@@ -16,84 +16,15 @@
 
 namespace hsr {
 
-// observe_hist (src/hist.cpp:8-14) at streaming speed. Counters live in lane-private COLUMNS: word (bin, lane) sits at
-// bin * 32 + lane, so lane l only ever touches bank l — a warp's 32 increments never share a bank, whatever the bytes
-// are, and every shared-memory atomic is one conflict-free request (round 1's one-histogram-per-warp layout pays one
-// pass per distinct word of the busiest bank: 2.6-3.0 TB/s on Zipf(1)/uniform bytes; this layout 3.6 TB/s on any input,
-// bound by the ~2.3 cycles a conflict-free ATOMS costs the SM's shared-memory pipe; profiles/r2/ubench_hist.jsonl).
-// The two warps of a CTA share the 32 KB plane through the u16 halves of each word (warp w adds 1 << 16 w); a thread
-// counts at most kObsEpochVecs * 16 < 65536 bytes between two flushes, so a half can never overflow into its neighbour.
-constexpr int kObsThreads = 64;
-constexpr int kObsInflight = 4;       // 16-byte loads requested per lane before the first is counted
-constexpr int kObsEpochVecs = 4032;   // 64,512 bytes per thread and epoch
-constexpr int kObsPlaneBytes = 256 * 32 * 4;
-
-__device__ __forceinline__ void obs_count16(uint32_t base, uint32_t inc, const uint4 &q)
+// observe_hist (src/hist.cpp:8-14) at streaming speed: see cta_count (hsr_hist_device.cuh)
+__global__ void __launch_bounds__(kCntThreads) observe_kernel(const uint8_t *data, uint64_t size, uint32_t *hist)
 {
-  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-      const uint32_t byte = __byte_perm(w[j], 0, 0x4440 + b);
-      asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(byte * 128u + base), "r"(inc) : "memory");
-    }
-  }
-}
-
-__global__ void __launch_bounds__(kObsThreads) observe_kernel(const uint8_t *data, uint64_t size, uint32_t *hist)
-{
-  extern __shared__ __align__(16) uint32_t sPlane[]; // [256 bins][32 lanes], u16 halves per warp
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint32_t sBase = (uint32_t)__cvta_generic_to_shared(sPlane);
-  const uint32_t base = sBase + lane * 4u;
-  const uint32_t inc = 1u << (16u * warp);
-
-  uint64_t head = (16u - (reinterpret_cast<uintptr_t>(data) & 15u)) & 15u; // bytes before the first 16-byte boundary
-  if (head > size) head = size;
-  const uint4 *v = reinterpret_cast<const uint4 *>(data + head);
-  const uint64_t vecs = (size - head) / 16;
-  const uint64_t stride = (uint64_t)gridDim.x * kObsThreads;
-  uint32_t total[4] = {0, 0, 0, 0}; // this thread's bins tid, tid + 64, tid + 128, tid + 192 over all epochs
-
-  uint64_t i = (uint64_t)blockIdx.x * kObsThreads + tid;
-  bool first = true;
-  do {
-    for (uint32_t k = tid; k < 256u * 32u; k += kObsThreads) sPlane[k] = 0;
-    __syncthreads();
-    if (first && blockIdx.x == 0) { // the unaligned head and tail bytes: CTA 0, once (fewer than 32 bytes in all)
-      if (tid < head) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((uint32_t)data[tid] * 128u + base), "r"(inc) : "memory");
-      const uint64_t done = head + vecs * 16;
-      if (tid < size - done) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((uint32_t)data[done + tid] * 128u + base), "r"(inc) : "memory");
-    }
-    first = false;
-    for (uint32_t e = 0; e < (uint32_t)kObsEpochVecs && i < vecs; e += kObsInflight, i += stride * kObsInflight) {
-      uint4 q[kObsInflight];
-#pragma unroll
-      for (int u = 0; u < kObsInflight; u++)
-        if (i + u * stride < vecs) q[u] = __ldg(v + i + u * stride);
-#pragma unroll
-      for (int u = 0; u < kObsInflight; u++)
-        if (i + u * stride < vecs) obs_count16(base, inc, q[u]);
-    }
-    __syncthreads();
-    // bin b: 32 lane words, read with a rotation that keeps the CTA's threads out of each other's banks
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-      const uint32_t b = tid + 64u * t;
-      uint32_t sum = 0;
-#pragma unroll 8
-      for (uint32_t j = 0; j < 32u; j++) {
-        const uint32_t w = sPlane[b * 32u + ((j + tid) & 31u)];
-        sum += (w & 0xffffu) + (w >> 16);
-      }
-      total[t] += sum;
-    }
-    __syncthreads();
-  } while (__syncthreads_or(i < vecs)); // another epoch only for inputs beyond 64,512 bytes per thread
+  extern __shared__ __align__(16) uint32_t sPlane[];
+  uint32_t total[4];
+  cta_count(data, size, blockIdx.x, gridDim.x, sPlane, total);
 #pragma unroll
   for (int t = 0; t < 4; t++)
-    if (total[t]) atomicAdd(hist + tid + 64 * t, total[t]);
+    if (total[t]) atomicAdd(hist + threadIdx.x + 64 * t, total[t]);
 }
 
 __global__ void __launch_bounds__(kHistThreads) normalize_kernel(const uint32_t *hist, uint64_t dataBytes, int bits,
@@ -107,21 +38,56 @@ __global__ void __launch_bounds__(kHistThreads) normalize_kernel(const uint32_t 
   cta_normalize(sHist, dataBytes, bits, sCapped, sIdx, symbolCount, cumul);
 }
 
-// one WARP per segment: count the segment's bytes, normalise, write its 256 u16 counts
-constexpr int kSegWarps = 4;
-__global__ void __launch_bounds__(kSegWarps * 32) segments_kernel(const uint8_t *data, uint64_t size, uint64_t segmentBytes, int bits,
-                                                                  uint16_t *symbolCounts)
+// per-range histograms in two steps: raw counts by one 64-thread CTA per range (conflict-free columns), then the
+// order-dependent normalisation with one LANE per range (hsr_hist_device.cuh). Round 1 gave a warp to each range and
+// parked 31 lanes behind lane 0's heap-sort: 1.19 ms per GB of 64 KiB segments, most of it one-lane shared-memory
+// requests that occupy the SM's data pipe like full ones.
+__global__ void __launch_bounds__(kCntThreads) seg_count_kernel(const uint8_t *data, SegPlan pl, uint32_t *counts32)
 {
-  __shared__ uint32_t sHist[kSegWarps][256];
-  __shared__ uint16_t sCapped[kSegWarps][256];
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint64_t segments = (size + segmentBytes - 1) / segmentBytes;
-  for (uint64_t seg = (uint64_t)blockIdx.x * kSegWarps + warp; seg < segments; seg += (uint64_t)gridDim.x * kSegWarps) {
-    const uint64_t begin = seg * segmentBytes;
-    const uint64_t end = begin + segmentBytes < size ? begin + segmentBytes : size;
-    warp_observe(data, begin, end, sHist[warp], lane);
-    warp_normalize(sHist[warp], end - begin, bits, sCapped[warp], sHist[warp], symbolCounts + seg * 256, lane);
+  extern __shared__ __align__(16) uint32_t sPlane[];
+  cta_count_ranges(data, pl, counts32, sPlane);
+}
+
+__global__ void __launch_bounds__(32) seg_normalize_kernel(const uint32_t *counts32, SegPlan pl, int bits, uint16_t *symbolCounts)
+{
+  extern __shared__ __align__(16) uint8_t sNorm[];
+  warp_normalize_ranges(counts32, pl, bits, symbolCounts, sNorm);
+}
+
+// host-side launchers, shared with the device encoder (hsr_encode.cu)
+static bool configure_range_kernels(int *smsOut)
+{
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  *smsOut = sms;
+  static bool configured[64] = {false};
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    if (cudaFuncSetAttribute(seg_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCntPlaneBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(seg_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneNormSmemBytes) != cudaSuccess)
+      return false;
+    configured[dev] = true;
   }
+  return true;
+}
+
+bool launch_range_counts(const uint8_t *dData, const SegPlan &pl, uint32_t *dCounts32, cudaStream_t st)
+{
+  int sms;
+  if (!configure_range_kernels(&sms)) return false;
+  const unsigned gridC = (unsigned)(pl.num < (uint64_t)sms * 6 ? pl.num : (uint64_t)sms * 6);
+  seg_count_kernel<<<gridC, kCntThreads, kCntPlaneBytes, st>>>(dData, pl, dCounts32);
+  return cudaGetLastError() == cudaSuccess;
+}
+
+bool launch_range_histograms(const uint8_t *dData, const SegPlan &pl, int bits, uint32_t *dCounts32, uint16_t *dCounts, cudaStream_t st)
+{
+  int sms;
+  if (!configure_range_kernels(&sms) || !launch_range_counts(dData, pl, dCounts32, st)) return false;
+  const uint64_t warps = ((uint64_t)pl.num + 31) / 32;
+  const unsigned gridN = (unsigned)(warps < (uint64_t)sms * 4 ? warps : (uint64_t)sms * 4);
+  seg_normalize_kernel<<<gridN, 32, kLaneNormSmemBytes, st>>>(dCounts32, pl, bits, dCounts);
+  return cudaGetLastError() == cudaSuccess;
 }
 
 } // namespace hsr
@@ -138,15 +104,15 @@ extern "C" int hsr_observe_hist_device(const void *dData, size_t size, uint32_t 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // persistent CTAs: six 33 KB CTAs (32 KB plane + the 1 KB every CTA reserves) fill an SM's shared memory
-  static int configured[64] = {0};
+  static bool configured[64] = {false};
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    if (cudaFuncSetAttribute(observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kObsPlaneBytes) != cudaSuccess) return -2;
-    configured[dev] = 1;
+    if (cudaFuncSetAttribute(observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCntPlaneBytes) != cudaSuccess) return -2;
+    configured[dev] = true;
   }
-  const uint64_t per = (uint64_t)kObsThreads * 16 * kObsInflight;
+  const uint64_t per = (uint64_t)kCntThreads * 16 * kCntInflight;
   uint64_t grid = (size + per - 1) / per;
   if (grid > (uint64_t)sms * 6) grid = (uint64_t)sms * 6;
-  observe_kernel<<<(unsigned)grid, kObsThreads, kObsPlaneBytes, st>>>(static_cast<const uint8_t *>(dData), size, dHist);
+  observe_kernel<<<(unsigned)grid, kCntThreads, kCntPlaneBytes, st>>>(static_cast<const uint8_t *>(dData), size, dHist);
   return cudaGetLastError() == cudaSuccess ? 1 : -2;
 }
 
@@ -162,15 +128,18 @@ extern "C" int hsr_make_hist_segments_device(const void *dData, size_t size, siz
                                              uint16_t *dSymbolCounts, void *cudaStream)
 {
   if (!dData || !dSymbolCounts || size == 0 || segmentBytes == 0 || bits < 1 || bits > 15) return -1;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const uint64_t segments = (size + segmentBytes - 1) / segmentBytes;
-  const uint64_t ctas = (segments + kSegWarps - 1) / kSegWarps;
-  const unsigned grid = (unsigned)(ctas < (uint64_t)sms * 16 ? ctas : (uint64_t)sms * 16);
-  segments_kernel<<<grid, kSegWarps * 32, 0, static_cast<cudaStream_t>(cudaStream)>>>(static_cast<const uint8_t *>(dData), size, segmentBytes,
-                                                                                bits, dSymbolCounts);
-  return cudaGetLastError() == cudaSuccess ? 1 : -2;
+  if (segments > 0x7fffffffull) return -1;
+  cudaStream_t st = static_cast<cudaStream_t>(cudaStream);
+  uint32_t *dCounts32 = nullptr; // stream-ordered scratch: the raw counts between the two kernels
+  if (cudaMallocAsync(&dCounts32, segments * 1024, st) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return -2;
+  }
+  SegPlan pl{nullptr, nullptr, (uint64_t)segmentBytes, (uint64_t)size, (uint32_t)segments};
+  const bool ok = launch_range_histograms(static_cast<const uint8_t *>(dData), pl, bits, dCounts32, dSymbolCounts, st);
+  cudaFreeAsync(dCounts32, st);
+  return ok ? 1 : -2;
 }
 
 extern "C" int hsr_make_hist(const uint8_t *pData, size_t size, int bits, uint16_t symbolCount[256], uint16_t cumul[256])
