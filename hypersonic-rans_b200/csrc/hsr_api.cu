@@ -10,6 +10,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -1011,6 +1012,35 @@ struct InFlight {
   std::vector<uint64_t> ends;
 };
 
+// HSR_TRACE_PIPELINE=1: device timestamps of every copy piece and range of one host-pointer decode, printed to stderr
+// when the call ends (diagnostics for the three-stream pipeline; timing events are only created when it is set).
+struct PipeTrace {
+  bool on = false;
+  cudaEvent_t t0 = nullptr;
+  struct Mark { const char *what; size_t index; uint64_t bytes; cudaEvent_t ev; };
+  std::vector<Mark> marks;
+  static bool enabled() { static const bool e = getenv("HSR_TRACE_PIPELINE") != nullptr; return e; }
+  void start(cudaStream_t s) { on = enabled(); if (on) { cudaEventCreate(&t0); cudaEventRecord(t0, s); } }
+  void mark(const char *what, size_t index, uint64_t bytes, cudaStream_t s)
+  {
+    if (!on) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s);
+    marks.push_back(Mark{what, index, bytes, e});
+  }
+  void dump()
+  {
+    if (!on) return;
+    for (const Mark &m : marks) {
+      float ms = 0; cudaEventElapsedTime(&ms, t0, m.ev);
+      fprintf(stderr, "[hsr pipeline] %8.3f ms  %-10s %3zu  %llu bytes\n", ms, m.what, m.index, (unsigned long long)m.bytes);
+      cudaEventDestroy(m.ev);
+    }
+    cudaEventDestroy(t0);
+    marks.clear(); on = false;
+  }
+};
+static thread_local PipeTrace g_trace;
+
 static bool start_h2d(DeviceCtx *c, const uint8_t *in, uint64_t lo, uint64_t hi, InFlight *fl)
 {
   // pieces grow 2, 2, 4, 8, 16, 16, ... MiB: the first decode launch waits for 2 MiB instead of 16 (0.04 ms instead of
@@ -1021,12 +1051,14 @@ static bool start_h2d(DeviceCtx *c, const uint8_t *in, uint64_t lo, uint64_t hi,
   fl->ends.clear();
   if (!grow(c->dIn, c->inCap, (size_t)(hi - lo) + 16)) return false;
   uint64_t a = lo;
+  g_trace.start(c->sIn);
   for (size_t k = 0; a < hi; k++) {
-    const uint64_t piece = fixedPiece ? fixedPiece : std::min<uint64_t>(16ull << 20, (2ull << 20) << (k > 0 ? k - 1 : 0));
+    const uint64_t piece = fixedPiece ? fixedPiece : (2ull << 20) << std::min<size_t>(k > 0 ? k - 1 : 0, 3);
     const uint64_t b = std::min(hi, a + piece);
     if (!ensure_events(c, k + 1)) return false;
     CU_TRY(cudaMemcpyAsync(c->dIn + (a - lo), in + a, (size_t)(b - a), cudaMemcpyHostToDevice, c->sIn), return false);
     CU_TRY(cudaEventRecord(c->evIn[k], c->sIn), return false);
+    g_trace.mark("h2d end", k, b - a, c->sIn);
     fl->ends.push_back(b);
     a = b;
   }
@@ -1075,12 +1107,16 @@ struct UnitPipeline {
     CU_TRY(cudaStreamWaitEvent(c->sRun, c->evIn[piece], 0), return false);
     uint64_t rangeDecoded = 0;
     for (size_t k = 0; k < count; k++) rangeDecoded += units[k].count;
+    g_trace.mark("run start", ranges, count, c->sRun);
     if (launch_units(family, N, bits, c->dIn, fl->lo, c->dOut, outLo, units, (uint32_t)count, c->dCounters + 1, c->sRun, nullptr, rangeDecoded) < 0)
       return false;
     CU_TRY(cudaEventRecord(c->evRun[ranges], c->sRun), return false);
+    g_trace.mark("run end", ranges, rangeDecoded, c->sRun);
     CU_TRY(cudaStreamWaitEvent(c->sOut, c->evRun[ranges], 0), return false);
     const uint64_t oLo = units[0].outOffset, oHi = units[count - 1].outOffset + units[count - 1].count;
+    g_trace.mark("d2h start", ranges, 0, c->sOut);
     CU_TRY(cudaMemcpyAsync(out + oLo, c->dOut + (oLo - outLo), (size_t)(oHi - oLo), cudaMemcpyDeviceToHost, c->sOut), return false);
+    g_trace.mark("d2h end", ranges, oHi - oLo, c->sOut);
     ranges++;
     return true;
   }
@@ -1095,6 +1131,7 @@ struct UnitPipeline {
     if (cudaStreamSynchronize(c->sOut) != cudaSuccess) ok = false;
     if (cudaStreamSynchronize(c->sIn) != cudaSuccess) ok = false;
     if (cudaStreamSynchronize(c->sRun) != cudaSuccess) ok = false;
+    g_trace.dump();
     if (!ok) { set_err("CUDA stream failed: %s", cudaGetErrorString(cudaGetLastError())); return false; }
     if (status[1]) { set_err("malformed stream (device status 0x%x)", status[1]); return false; }
     return true;

@@ -33,4 +33,23 @@ for key in sorted(z4.files):
     print(key, "ok" if ok else "MISMATCH")
 cnt, cum = pkg.make_hist(z["in/multi"], 12)
 print("hist ok", np.array_equal(cnt, z["hist/multi/12"][0]))
+# round 2: per-range histograms (counter columns + one lane per histogram) on odd ranges, and the device encoders
+import torch
+data = z["in/multi"]
+d = torch.from_numpy(np.ascontiguousarray(data)).cuda()
+for seg, off in ((4099, 3), (65536, 0), (17, 1)):
+    nbytes = min(data.size - off, seg * 37 + 5)
+    nseg = (nbytes + seg - 1) // seg
+    counts = torch.zeros((nseg, 256), dtype=torch.int16, device="cuda")
+    rc = pkg.make_hist_segments_device(d.data_ptr() + off, nbytes, seg, 13, counts.data_ptr(), 0)
+    torch.cuda.synchronize()
+    print("segments", seg, off, "rc", rc)
+    bad += rc <= 0
+for states, bits in ((32, 10), (64, 15)):
+    for fn in (pkg.encode_mt, pkg.encode_mt_policy):
+        stream = fn(states, bits, data, 0)
+        n, out = pkg.decode(2, states, bits, stream, data.size)
+        ok = n == data.size and np.array_equal(out[:n], data)
+        bad += not ok
+        print("encoder", fn.__name__, states, bits, "ok" if ok else "MISMATCH")
 sys.exit(1 if bad else 0)

@@ -257,6 +257,57 @@ def test_observe_hist_device_counts(gpu):
     assert np.array_equal(hist.cpu().numpy().astype(np.int64), np.bincount(data[3:], minlength=256))
 
 
+def test_histogram_counter_columns_edges(gpu):
+    """The lane-private u16 counter halves are flushed every 64,512 bytes per thread: ranges long enough for several
+    epochs, a constant input (one bin takes every increment of every thread), odd segment sizes with unaligned starts,
+    and inputs shorter than one 16-byte vector must all count exactly (src/hist.cpp:8-14) and normalise like the
+    reference (:16-215)."""
+    import torch
+    st = torch.cuda.current_stream().cuda_stream
+    # 1. one 9.4 MB range = 2.3 epochs of a 64-thread CTA; 20,000,003 bytes -> 3 ranges, the last one short and odd
+    data = _zipf(gpu, 20_000_003, 1.0, 21, 0)
+    d = torch.from_numpy(data).cuda()
+    seg = 9_437_187
+    nseg = (data.size + seg - 1) // seg
+    counts = torch.zeros((nseg, 256), dtype=torch.int16, device="cuda")
+    assert gpu.make_hist_segments_device(d.data_ptr(), data.size, seg, 15, counts.data_ptr(), st) > 0
+    torch.cuda.synchronize()
+    got = counts.cpu().numpy().view(np.uint16)
+    for k in range(nseg):
+        want, _ = ck.oracle_make_hist(data[k * seg:(k + 1) * seg], 15)
+        assert np.array_equal(got[k], want), k
+    # 2. constant bytes: every thread hammers one bin; 6,000,000 bytes on one CTA range is 93,750 per thread (two epochs)
+    const = np.full(6_000_000, 0xA7, np.uint8)
+    dc = torch.from_numpy(const).cuda()
+    hist = torch.zeros(256, dtype=torch.int32, device="cuda")
+    assert gpu.observe_hist_device(dc.data_ptr(), const.size, hist.data_ptr(), st) > 0
+    torch.cuda.synchronize()
+    assert int(hist[0xA7]) == const.size and int(hist.sum()) == const.size
+    c1 = torch.zeros((1, 256), dtype=torch.int16, device="cuda")
+    assert gpu.make_hist_segments_device(dc.data_ptr(), const.size, const.size, 12, c1.data_ptr(), st) > 0
+    torch.cuda.synchronize()
+    want, _ = ck.oracle_make_hist(const, 12)
+    assert np.array_equal(c1.cpu().numpy().view(np.uint16)[0], want)
+    # 3. odd segment sizes from an unaligned base, and inputs below one vector
+    small = _zipf(gpu, 70_001, 0.7, 22, 0)
+    ds = torch.from_numpy(small).cuda()
+    for seg, off in ((1, 0), (7, 1), (15, 3), (16, 5), (17, 2), (333, 7), (4099, 9)):
+        n = min(small.size - off, seg * 40 + 5)
+        nseg = (n + seg - 1) // seg
+        cs = torch.zeros((nseg, 256), dtype=torch.int16, device="cuda")
+        assert gpu.make_hist_segments_device(ds.data_ptr() + off, n, seg, 11, cs.data_ptr(), st) > 0
+        torch.cuda.synchronize()
+        got = cs.cpu().numpy().view(np.uint16)
+        for k in range(nseg):
+            want, _ = ck.oracle_make_hist(small[off + k * seg: off + min(n, (k + 1) * seg)], 11)
+            assert np.array_equal(got[k], want), (seg, off, k)
+    for n in (1, 2, 15, 16, 17, 31, 33):
+        hist.zero_()
+        assert gpu.observe_hist_device(ds.data_ptr() + 1, n, hist.data_ptr(), st) > 0
+        torch.cuda.synchronize()
+        assert np.array_equal(hist.cpu().numpy().astype(np.int64), np.bincount(small[1:1 + n], minlength=256)), n
+
+
 def test_full_size_100mb_round_trip(gpu):
     """BASELINE.json sizes: 100,000,000-byte Zipf stream; decode(encode(x)) == x for configs 1-3 and the mt_ codec."""
     n = 100_000_000

@@ -193,9 +193,11 @@ def test_concurrent_host_threads_overlap_on_one_device(gpu):
         assert np.array_equal(hout.array, data)
     print(f"\n4 x 100 MB mt_64x15 host decodes: serial {t_serial * 1e3:.1f} ms, 4 threads {t_parallel * 1e3:.1f} ms, "
           f"ratio {t_serial / t_parallel:.2f}")
-    # One call already overlaps its own H2D, kernels and D2H; what the pool adds is the fill and drain of each call's
-    # pipeline hidden behind its neighbours'. PCIe bounds the rest (both directions busy in either mode).
-    assert t_parallel < t_serial / 1.15, (t_serial, t_parallel)
+    # One call already overlaps its own H2D, kernels and D2H (and starts its first range ~0.1 ms into the call), so the
+    # serial loop runs at ~37 GB/s of the box's ~51 GB/s duplex PCIe ceiling (profiles/r2/pcie_probe_nway.jsonl). What
+    # the pool adds is the fill and drain of each call hidden behind its neighbours': up to 51 / 37 = 1.38x, never the
+    # K-fold gain of K CPU threads. The assertion is that the calls do overlap (a whole-call mutex gives 1.00).
+    assert t_parallel < t_serial / 1.05, (t_serial, t_parallel)
     for _, _, hin, hout in bufs:
         hin.free(); hout.free()
 
