@@ -59,6 +59,27 @@ def _stage(msg):
 _T0 = time.time()
 
 
+# The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints "NCCL version ..." from C, past
+# sys.stdout), so the real stdout is kept aside for that line and file descriptor 1 is pointed at stderr for everything
+# else this process or its libraries print.
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def _emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -236,7 +257,7 @@ def run_reference(a, rank, world):
         "gpu_launches": 0,
         "loaded_libraries": sorted({os.path.basename(l.split()[-1]) for l in open("/proc/self/maps") if "libhs" in l}),
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def time_decode(torch, ps, out_ptr, cap, reps, shard_local=False):
@@ -410,6 +431,7 @@ def other_configs(pkg, torch, a, peak, heavy):
 
 def main():
     a = parse_args()
+    _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -550,10 +572,10 @@ def main():
 
     if a.kernel_only:
         if rank == 0:
-            print(json.dumps({"kernel_only": True, "value": round(value, 3), "unit": "GB/s", "ms_per_step": round(ms_per_step, 4),
+            _emit({"kernel_only": True, "value": round(value, 3), "unit": "GB/s", "ms_per_step": round(ms_per_step, 4),
                               "serialized_GBps": round(n / serial_ms / 1e6, 3), "serialized_ms": round(serial_ms, 4),
                               "bits": a.bits, "states": a.states, "table": a.table, "ctas_per_sm": a.ctas_per_sm, "blocks": units, "compressed": comp,
-                              "n_gpus": world, "traffic_GBps": round((comp + n) / (ms_per_step * 1e-3) / 1e9, 1), "clocks": clocks}), flush=True)
+                              "n_gpus": world, "traffic_GBps": round((comp + n) / (ms_per_step * 1e-3) / 1e9, 1), "clocks": clocks})
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -709,7 +731,7 @@ def main():
         _stage('other configs')
         if not a.headline_only:
             line["other_configs"] = other_configs(pkg, torch, a, peak, a.extra)
-        print(json.dumps(line), flush=True)
+        _emit(line)
     ps.free()
     if world > 1:
         host_barrier()

@@ -5,8 +5,10 @@
 // four 16-byte coalesced loads in flight per lane, one global atomicAdd per bin per CTA at the end.
 // normalise: 256 elements of order-dependent integer logic. The float scale is done with explicit round-to-
 // nearest MUL and ADD (never an FMA — the reference build has no FMA target, src/hist.cpp:60-64); the index
-// heap-sort and the steal/charity loops (:105-198) run literally, on one thread, because the tie order of that
-// particular unstable sort decides which symbols receive the +-1.
+// heap-sort and the steal/charity loops (:105-198) run literally, one thread per histogram, because the tie order of
+// that particular unstable sort decides which symbols receive the +-1 (one histogram: thread 0 of a CTA; the
+// per-block histograms of the block_/mt_ encoders: one LANE each, 32 histograms per warp).
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <cuda_runtime.h>
@@ -61,7 +63,7 @@ static bool configure_range_kernels(int *smsOut)
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   *smsOut = sms;
-  static bool configured[64] = {false};
+  static std::atomic<bool> configured[64]; // zero-initialised; setting the attribute twice is harmless
   if (dev >= 0 && dev < 64 && !configured[dev]) {
     if (cudaFuncSetAttribute(seg_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCntPlaneBytes) != cudaSuccess ||
         cudaFuncSetAttribute(seg_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneNormSmemBytes) != cudaSuccess)
@@ -104,7 +106,7 @@ extern "C" int hsr_observe_hist_device(const void *dData, size_t size, uint32_t 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // persistent CTAs: six 33 KB CTAs (32 KB plane + the 1 KB every CTA reserves) fill an SM's shared memory
-  static bool configured[64] = {false};
+  static std::atomic<bool> configured[64];
   if (dev >= 0 && dev < 64 && !configured[dev]) {
     if (cudaFuncSetAttribute(observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCntPlaneBytes) != cudaSuccess) return -2;
     configured[dev] = true;
