@@ -51,6 +51,20 @@
 #ifndef HSR_RING2
 #define HSR_RING2 1
 #endif
+//   HSR_GRP24       1: at 15 bits and N = 32 the bitmap-rank groups cover 24 slots instead of 16 ({8-bit prefix | 24-bit
+//                   bitmap} still fills one u32): the group table shrinks from 8 KB to 5.5 KB, so 26 instead of 20
+//                   one-warp CTAs fit an SM, for a multiply-shift division by 24 on the lookup path (symbol_step_rank).
+//                   N = 32 has one state per lane and is short of warps, not of pipe cycles: 660 -> 740 GB/s (723 -> 816
+//                   with overlapping launches). N = 64 (two states per lane, data-pipe-bound) gains nothing from the
+//                   extra warps and pays for the extra instructions (917 -> 839, 956 -> 964 overlapped), so it keeps
+//                   16-slot groups (profiles/r2/variants_grp24.jsonl).
+#ifndef HSR_GRP24
+#define HSR_GRP24 1
+#endif
+//   HSR_RING_TMA    1 (with HSR_RING2=0): the word ring is fed by TMA bulk copies (measured slower, see WordRingTma)
+#ifndef HSR_RING_TMA
+#define HSR_RING_TMA 0
+#endif
 //   HSR_QUAD_STORE  1: four half-rows of decoded bytes leave as one 32-bit store per lane after a 4x4 byte transpose
 //                   inside each lane quad (see rows_impl); 0: one byte store per lane and half-row
 #ifndef HSR_QUAD_STORE
@@ -148,8 +162,15 @@ struct WarpLayout {
                 "packed slot table up to 12 bits, wide slot tables from 13 bits");
 
   static constexpr int kSlots = 1 << BITS;
-  static constexpr int kGroups = kSlots / 16;       // bitmap-rank groups of 16 slots
+  // bitmap-rank groups: one u32 {symbol starts before the group | start bitmap of its slots} per kGrpSlots slots.
+  // 16 slots: {16 | 16}; 24 slots (15 bits, N = 32): {8 | 24} — at most 255 starts precede a group (slot 0's is implicit)
+  static constexpr int kGrpSlots = (HSR_GRP24 && BITS == 15 && N == 32) ? 24 : 16;
+  static constexpr int kPrefixShift = 32 - (kGrpSlots == 24 ? 8 : 16);
+  static constexpr int kGroupsUsed = (kSlots + kGrpSlots - 1) / kGrpSlots;
+  static constexpr int kGroups = kGrpSlots == 16 ? kGroupsUsed : (kGroupsUsed + 127) / 128 * 128; // scan granularity
   static constexpr int kGrpBytes = kGroups * 4;
+  // group of a slot; 43691 / 2^20 = 1 / 23.99983: exact floor(slot / 24) for every slot < 2^15
+  static __device__ __forceinline__ uint32_t grp_of(uint32_t slot) { return kGrpSlots == 16 ? slot >> 4 : (slot * 43691u) >> 20; }
   static constexpr int kEntBytes = 256 * 4;
   static constexpr int kSymBytes = 256;
   static constexpr int kPackedBytes = TK == TK_PACKED ? kSlots * 4 : 0;
@@ -170,8 +191,8 @@ struct WarpLayout {
   static constexpr int kOffWide = kOffPacked + kPackedBytes;
   static constexpr int kOffWideSym = kOffWide + (TK == TK_WIDE ? kSlots * 4 : 0);
   static constexpr int kOffRing = kOffWide + kWideBytes;
-  static constexpr int kOffBar = kOffRing + kRingBytes;   // one mbarrier per ring buffer (TMA bulk copies)
-  static constexpr int kOffTile = kOffBar + 32;           // output staging tile (HSR_OUT_TILE experiments)
+  static constexpr int kOffBar = kOffRing + kRingBytes;   // one mbarrier per ring buffer (TMA bulk copies only)
+  static constexpr int kOffTile = kOffBar + (HSR_RING_TMA ? 32 : 0); // output staging tile (HSR_OUT_TILE experiments)
   static constexpr int kTileBytes = HSR_OUT_TILE ? 512 : 0;
   static constexpr int kBytes = kOffTile + kTileBytes;    // per warp (= per CTA), multiple of 16
   static_assert(kBytes % 16 == 0 && kBytes <= (kDynamic ? 227 : 48) * 1024, "shared memory budget");
@@ -425,9 +446,6 @@ struct WordRingTma {
 // sizes) measured 726 GB/s against 903 for the two-buffer LDGSTS ring (profiles/r1/variants_ring_unroll.jsonl): small
 // bulk copies at ~3000 warps x 1 per 1.5 us are simply not what the TMA is good at. It stays available
 // (-DHSR_RING_TMA=1 -DHSR_RING2=0) for larger-segment experiments; LDGSTS is the default.
-#ifndef HSR_RING_TMA
-#define HSR_RING_TMA 0
-#endif
 template <class L>
 #if HSR_RING_TMA
 using Ring = WordRingTma<L>;
@@ -444,6 +462,16 @@ struct TableInfo {
   bool allPresent;  // every symbol has a non-zero count: rank == symbol
   bool degenerate;  // one symbol owns the whole range (freq == 2^BITS)
 };
+
+// rank of the symbol that owns `slot` (table expansion; the hot loop has its own fused form in symbol_step_rank)
+template <class L>
+__device__ __forceinline__ uint32_t rank_of_slot(uint32_t sGrp, uint32_t slot)
+{
+  const uint32_t g = L::grp_of(slot);
+  const uint32_t w = lds_u32(sGrp + (g << 2));
+  const uint32_t pos = slot - g * (uint32_t)L::kGrpSlots;
+  return (w >> L::kPrefixShift) + __popc(w << (31u - pos)); // starts at or below the slot
+}
 
 // Builds the warp's tables from 256 u16 counts at `counts` (2-byte aligned global memory). Warp-uniform result.
 template <int BITS, int N, int TK>
@@ -495,8 +523,10 @@ __device__ __forceinline__ TableInfo build_tables(uint32_t smemWarp, const uint8
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     if (freq[k]) {
-      if (cumul) // the start at slot 0 is implicit, so that (starts before or at a slot) == rank of its symbol
-        atoms_or(sGrp + ((cumul >> 4) << 2), 1u << (cumul & 15u));
+      if (cumul) { // the start at slot 0 is implicit, so that (starts before or at a slot) == rank of its symbol
+        const uint32_t g = L::grp_of(cumul);
+        atoms_or(sGrp + (g << 2), 1u << (cumul - g * (uint32_t)L::kGrpSlots));
+      }
       // x' = x + (x >> b) * (freq - 2^b) - cumul; both fields are signed 16-bit
       const uint32_t e = (((0u - cumul) & 0xffffu) << 16) | ((freq[k] - (uint32_t)L::kSlots) & 0xffffu);
       sts_u32(sEnt + rank * 4u, e);
@@ -526,7 +556,8 @@ __device__ __forceinline__ TableInfo build_tables(uint32_t smemWarp, const uint8
           scan += up;
       }
       const uint32_t e0 = carry + scan - tot, e1 = e0 + c0, e2 = e1 + c1, e3 = e2 + c2;
-      sts_v4(a, make_uint4((e0 << 16) | bm.x, (e1 << 16) | bm.y, (e2 << 16) | bm.z, (e3 << 16) | bm.w));
+      constexpr int kP = L::kPrefixShift;
+      sts_v4(a, make_uint4((e0 << kP) | bm.x, (e1 << kP) | bm.y, (e2 << kP) | bm.z, (e3 << kP) | bm.w));
       carry += __shfl_sync(kFull, scan, 31);
     }
   } else
@@ -542,7 +573,7 @@ __device__ __forceinline__ TableInfo build_tables(uint32_t smemWarp, const uint8
       if (lane >= (uint32_t)d)
         scan += up;
     }
-    sts_u32(a, ((carry + scan - c) << 16) | bm);
+    sts_u32(a, ((carry + scan - c) << L::kPrefixShift) | bm);
     carry += __shfl_sync(kFull, scan, 31);
   }
   __syncwarp();
@@ -551,8 +582,7 @@ __device__ __forceinline__ TableInfo build_tables(uint32_t smemWarp, const uint8
     // expand to one u32 per slot: {freq:12 | symbol:8 | slot - cumul:12}
     const uint32_t sPk = smemWarp + L::kOffPacked;
     for (uint32_t slot = lane; slot < (uint32_t)L::kSlots; slot += 32u) {
-      const uint32_t g = lds_u32(sGrp + ((slot >> 4) << 2));
-      const uint32_t rank = (g >> 16) + __popc(g << (31u - (slot & 15u)));
+      const uint32_t rank = rank_of_slot<L>(sGrp, slot);
       const uint32_t e = lds_u32(sEnt + rank * 4u);
       const uint32_t s = lds_u8(sSym + rank);
       const uint32_t f = (uint32_t)L::kSlots + (uint32_t)(int32_t)(int16_t)(e & 0xffffu);
@@ -565,8 +595,7 @@ __device__ __forceinline__ TableInfo build_tables(uint32_t smemWarp, const uint8
     // expand to {freq:16 | slot - cumul:16} and the symbol per slot
     const uint32_t sW = smemWarp + L::kOffWide, sWs = smemWarp + L::kOffWideSym;
     for (uint32_t slot = lane; slot < (uint32_t)L::kSlots; slot += 32u) {
-      const uint32_t g = lds_u32(sGrp + ((slot >> 4) << 2));
-      const uint32_t rank = (g >> 16) + __popc(g << (31u - (slot & 15u)));
+      const uint32_t rank = rank_of_slot<L>(sGrp, slot);
       const uint32_t e = lds_u32(sEnt + rank * 4u);
       const uint32_t f = (uint32_t)L::kSlots + (uint32_t)(int32_t)(int16_t)(e & 0xffffu);
       const uint32_t bias = (slot + (uint32_t)((int32_t)e >> 16)) & 0xffffu;
@@ -601,10 +630,21 @@ struct Decoder {
   template <bool kAllPresent>
   __device__ __forceinline__ uint32_t symbol_step_rank(uint32_t &x) const
   {
-    const uint32_t g = lds_u32(sGrp + ((x >> 2) & (uint32_t)((L::kGroups - 1) << 2)));
-    uint32_t sh; // 31 - (x & 15) = (~x & 15) | 16 as ONE lop3 (immLut 0xAE = (~a & b) | c)
-    asm("lop3.b32 %0, %1, 15, 16, 0xAE;" : "=r"(sh) : "r"(x));
-    const uint32_t rank = (g >> 16) + __popc(g << sh); // symbol starts at or below the slot = rank of its owner
+    uint32_t rank; // symbol starts at or below the slot = rank of its owner
+    if constexpr (L::kGrpSlots == 16) {
+      const uint32_t g = lds_u32(sGrp + ((x >> 2) & (uint32_t)((L::kGroups - 1) << 2)));
+      uint32_t sh; // 31 - (x & 15) = (~x & 15) | 16 as ONE lop3 (immLut 0xAE = (~a & b) | c)
+      asm("lop3.b32 %0, %1, 15, 16, 0xAE;" : "=r"(sh) : "r"(x));
+      rank = (g >> 16) + __popc(g << sh);
+    } else {
+      // 24-slot groups: gi = slot / 24 by multiply-shift; the bit position is pos = slot - 24 gi, and the shift that
+      // brings bit `pos` to bit 31, 31 - pos, equals (24 gi + ~x) mod 32 (x = slot mod 32) — one multiply-add feeding a
+      // wrapping funnel shift, no subtraction, no mask
+      const uint32_t gi = ((x & (uint32_t)(L::kSlots - 1)) * 43691u) >> 20;
+      const uint32_t g = lds_u32(sGrp + (gi << 2));
+      const uint32_t sh = gi * 24u + ~x;
+      rank = (g >> 24) + __popc(__funnelshift_l(0u, g, sh));
+    }
     const uint32_t e = lds_u32(sEnt + rank * 4u);
     x = (x >> BITS) * (uint32_t)(int32_t)(int16_t)(e & 0xffffu) + x; // (x >> b) * freq + slot
     x += (uint32_t)((int32_t)e >> 16);                               // - cumul
