@@ -332,6 +332,18 @@ def other_configs(pkg, torch, a, peak, heavy):
                                  "frac": round((total + in_base.size) / ms / 1e6 / peak, 4)}
         ps.free()
         del out2
+        # the same batch end to end through the host-pointer call (hsr_decode_batch, pinned buffers): pieces of the input
+        # go up, groups of streams decode and come back as a pipeline
+        hin, hout = pkg.host_alloc(in_base.size), pkg.host_alloc(total)
+        hin.array[:] = in_base
+        pkg.decode_batch(fam, states, bits, hin.array, hout.array, items)   # warm-up: scratch, events
+        hout.array[:] = 0xCC
+        t0 = time.perf_counter()
+        n_ok, _ = pkg.decode_batch(fam, states, bits, hin.array, hout.array, items)
+        dt = time.perf_counter() - t0
+        res[label + "_batch"]["e2e_host_pointers"] = {"decoded_GBps": round(total / dt / 1e9, 2), "ms": round(dt * 1e3, 3),
+                                                      "bit_exact": bool(n_ok == k_streams and np.array_equal(hout.array, data))}
+        hin.free(); hout.free()
 
     # BASELINE config 4's low-parallelism shape: the reference encoder merges stationary (iid) data into ~32 MiB blocks
     # (src/mt_rANS32x64_16w_encode.cpp:207-213), i.e. ~60 independent warps of work per GB whatever the GPU

@@ -67,7 +67,7 @@ static R guarded(R onFail, F &&f) noexcept
   return onFail;
 }
 
-static std::atomic<long> g_optTable{0}, g_optWarps{0}, g_optChunkMb{0}, g_optIndex{0}, g_optOverlap{1}, g_optContexts{4};
+static std::atomic<long> g_optTable{0}, g_optWarps{0}, g_optChunkMb{0}, g_optIndex{0}, g_optOverlap{1}, g_optContexts{4}, g_optBatchGroupMb{0};
 
 // hsr_index.cu
 bool hsr_parallel_mt_index(const uint8_t *dIn, uint64_t compLen, uint64_t n, int N, int bits, std::vector<hsr_block_t> *out, float *ms);
@@ -101,6 +101,7 @@ extern "C" int hsr_set_option(const char *key, long value)
   if (!strcmp(key, "index")) { if (value < 0 || value > 2) return -1; g_optIndex = value; return 0; }
   if (!strcmp(key, "overlap")) { if (value < 0 || value > 1) return -1; g_optOverlap = value; return 0; }
   if (!strcmp(key, "contexts")) { if (value < 1 || value > 16) return -1; g_optContexts = value; return 0; }
+  if (!strcmp(key, "batch_group_mb")) { if (value < 0) return -1; g_optBatchGroupMb = value; return 0; }
   return -1;
 }
 
@@ -113,6 +114,7 @@ extern "C" long hsr_get_option(const char *key)
   if (!strcmp(key, "index")) return g_optIndex;
   if (!strcmp(key, "overlap")) return g_optOverlap;
   if (!strcmp(key, "contexts")) return g_optContexts;
+  if (!strcmp(key, "batch_group_mb")) return g_optBatchGroupMb;
   return -1;
 }
 
@@ -905,6 +907,7 @@ struct DeviceCtx {
   hsr_block_t *dBlocks = nullptr; size_t blocksCap = 0;
   hsr_block_t *hBlocks = nullptr; size_t hBlocksCap = 0; // pinned + mapped: kernels read the index straight from host memory
   uint32_t *dCounters = nullptr; size_t countersCap = 0; // 4 u32 per launch: block_ work counter, status, pad, pad
+  uint32_t *hStatus = nullptr; size_t hStatusCap = 0;    // pinned + mapped: per-stream status words of a batch, read by the host
   std::vector<cudaEvent_t> evIn, evRun;
 };
 
@@ -1287,67 +1290,141 @@ static size_t decode_batch_impl(int family, int N, int bits, const uint8_t *inBa
   if (!plan_batch(family, N, inBase, items, count, &plan)) return 0;
   std::vector<Header> &hdr = plan.hdr;
   std::vector<char> &good = plan.good;
-  std::vector<hsr_block_t> &units = plan.units;
-  std::vector<BlockStreamDesc> &descs = plan.descs;
-  std::vector<uint32_t> &descStream = plan.descStream;
   const uint64_t inLo = plan.inLo, inHi = plan.inHi, outLo = plan.outLo, outHi = plan.outHi;
 
-  if (!grow(c->dIn, c->inCap, (size_t)(inHi - inLo) + 16)) return 0;
-  if (!grow(c->dOut, c->outCap, (size_t)(outHi - outLo) + 16)) return 0;
-  if (!grow(c->dCounters, c->countersCap, 4 + count)) return 0; // [0] block_ work counter, [1] status, [4..] per-stream status
-  uint32_t *dStreamStatus = c->dCounters + 4;
-  CU_TRY(cudaMemsetAsync(c->dCounters, 0, (4 + count) * sizeof(uint32_t), c->sRun), return 0);
-  CU_TRY(cudaMemcpyAsync(c->dIn, inBase + inLo, (size_t)(inHi - inLo), cudaMemcpyHostToDevice, c->sRun), return 0);
-  if (family == HSR_BLOCK) {
-    const size_t bytes = descs.size() * sizeof(BlockStreamDesc);
-    if (!grow(c->dBlocks, c->blocksCap, bytes / sizeof(hsr_block_t) + 1)) return 0;
-    CU_TRY(cudaMemcpyAsync(c->dBlocks, descs.data(), bytes, cudaMemcpyHostToDevice, c->sRun), return 0);
-    // per-stream status is indexed by the position in `descs`; map back below
-    uint64_t batchDecoded = 0;
-    for (const auto &d : descs) batchDecoded += d.n;
-    if (launch_block_batch(N, bits, c->dIn, c->dOut, reinterpret_cast<const BlockStreamDesc *>(c->dBlocks), (uint32_t)descs.size(),
-                           c->dCounters, dStreamStatus, c->sRun, batchDecoded) < 0)
-      return 0;
-  } else {
-    if (!grow(c->dBlocks, c->blocksCap, units.size())) return 0;
-    std::stable_sort(units.begin(), units.end(), [](const hsr_block_t &a, const hsr_block_t &b) { return a.count > b.count; }); // longest first
-    CU_TRY(cudaMemcpyAsync(c->dBlocks, units.data(), units.size() * sizeof(hsr_block_t), cudaMemcpyHostToDevice, c->sRun), return 0);
-    uint64_t batchDecoded = 0;
-    for (const auto &u : units) batchDecoded += u.count;
-    if (launch_units(family, N, bits, c->dIn, inLo, c->dOut, outLo, c->dBlocks, (uint32_t)units.size(), c->dCounters + 1, c->sRun, dStreamStatus,
-                     batchDecoded) < 0)
-      return 0;
+  // The batch runs as a pipeline like a single mt_ stream does: streams are taken in input order and cut into groups
+  // of growing traffic (UnitPipeline::range_bytes); the whole input range goes to the device in pieces, every group is
+  // launched as soon as the piece holding its last byte has landed, and its decoded bytes go back while later groups
+  // decode. Per-stream status words live in mapped host memory, so the host can tell which streams of a finished group
+  // decoded cleanly (only those are copied back) without a device -> host copy in between.
+  std::vector<uint32_t> order; // well-formed streams by input offset
+  for (size_t i = 0; i < count; i++)
+    if (good[i]) order.push_back((uint32_t)i);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return items[x].inOffset < items[y].inOffset; });
+  std::vector<size_t> unitFirst(count + 1, 0); // plan.units / plan.descs hold the good streams in stream order
+  {
+    size_t at = 0, d = 0;
+    for (size_t i = 0; i < count; i++) {
+      unitFirst[i] = family == HSR_BLOCK ? d : at;
+      if (!good[i]) continue;
+      if (family == HSR_BLOCK) d++;
+      else while (at < plan.units.size() && plan.units[at].reserved == (uint32_t)i) at++;
+    }
+    unitFirst[count] = family == HSR_BLOCK ? d : at;
   }
-  std::vector<uint32_t> status(4 + count);
-  CU_TRY(cudaMemcpyAsync(status.data(), c->dCounters, (4 + count) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->sRun), return 0);
-  CU_TRY(cudaStreamSynchronize(c->sRun), return 0);
+  struct Group { size_t sa, sb, ua, ub; uint64_t needEnd, decoded; };
+  std::vector<Group> groups;
+  std::vector<hsr_block_t> su;          // units in launch order
+  std::vector<BlockStreamDesc> sd;      // block_ streams in launch order (position == index into `order`)
+  {
+    // A group's kernel cannot finish before its longest unit has been decoded by ONE warp (~0.4-0.8 GB/s), however
+    // few units it holds, and consecutive groups run one after another: a group must therefore carry enough bytes for
+    // its copies (~50 GB/s) to outlast that floor — 512 x its longest unit — or many small groups would serialise
+    // their floors (2368 raw streams of 400 KB in 37 groups: 35 ms; in 8 groups: the copies' 21 ms).
+    const long optGroupMb = g_optBatchGroupMb; // tests: a fixed group size instead of the rule above
+    Group g{0, 0, 0, 0, 0, 0};
+    uint64_t acc = 0, longest = 0;
+    for (size_t k = 0; k < order.size(); k++) {
+      const uint32_t i = order[k];
+      if (family == HSR_BLOCK) {
+        sd.push_back(plan.descs[unitFirst[i]]);
+        longest = std::max<uint64_t>(longest, hdr[i].n);
+      } else {
+        for (size_t u = unitFirst[i]; u < unitFirst[i + 1]; u++) {
+          su.push_back(plan.units[u]);
+          if (plan.units[u].kind != 1u) longest = std::max<uint64_t>(longest, plan.units[u].count);
+        }
+      }
+      g.needEnd = std::max<uint64_t>(g.needEnd, items[i].inOffset + hdr[i].compLen);
+      g.decoded += hdr[i].n;
+      acc += hdr[i].compLen + hdr[i].n;
+      const uint64_t target = optGroupMb > 0 ? (uint64_t)optGroupMb << 20 : std::max<uint64_t>(UnitPipeline::range_bytes(groups.size()), 512 * longest);
+      if (acc >= target || k + 1 == order.size()) {
+        g.sb = k + 1;
+        g.ub = family == HSR_BLOCK ? k + 1 : su.size();
+        if (family != HSR_BLOCK) // longest units first inside a group
+          std::stable_sort(su.begin() + (long)g.ua, su.begin() + (long)g.ub, [](const hsr_block_t &x, const hsr_block_t &y) { return x.count > y.count; });
+        groups.push_back(g);
+        g = Group{k + 1, k + 1, g.ub, g.ub, 0, 0};
+        acc = 0;
+        longest = 0;
+      }
+    }
+  }
 
-  // copy back only streams that decoded cleanly, merging runs whose outputs are contiguous
+  auto fail = [&]() -> size_t { cudaStreamSynchronize(c->sIn); cudaStreamSynchronize(c->sRun); cudaStreamSynchronize(c->sOut); return 0; };
+  // the unit list goes up FIRST: a copy queued behind the input pieces would wait for all of them on the copy engine
+  // (and with it every launch: measured, the first group then starts after the whole 14 ms of input)
+  const size_t listBytes = family == HSR_BLOCK ? sd.size() * sizeof(BlockStreamDesc) : su.size() * sizeof(hsr_block_t);
+  if (!grow(c->dBlocks, c->blocksCap, listBytes / sizeof(hsr_block_t) + 1)) return 0;
+  CU_TRY(cudaMemcpyAsync(c->dBlocks, family == HSR_BLOCK ? (const void *)sd.data() : (const void *)su.data(), listBytes, cudaMemcpyHostToDevice, c->sRun),
+         return fail());
+  CU_TRY(cudaStreamSynchronize(c->sRun), return fail()); // su / sd are pageable: the copy has read them when this returns
+  InFlight fl;
+  if (!start_h2d(c, inBase, inLo, inHi, &fl)) return fail();
+  if (!grow(c->dOut, c->outCap, (size_t)(outHi - outLo) + 16)) return fail();
+  if (!grow(c->dCounters, c->countersCap, 4)) return fail();
+  if (count > c->hStatusCap) {
+    if (c->hStatus) cudaFreeHost(c->hStatus);
+    c->hStatus = nullptr; c->hStatusCap = 0;
+    const size_t want = count + count / 4 + 256;
+    CU_TRY(cudaHostAlloc(&c->hStatus, want * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable), return fail());
+    c->hStatusCap = want;
+  }
+  memset(c->hStatus, 0, count * sizeof(uint32_t)); // raw / mt_: indexed by stream; block_: by position in `order`
+  CU_TRY(cudaMemsetAsync(c->dCounters, 0, 16, c->sRun), return fail());
+  while (c->evRun.size() < groups.size()) {
+    cudaEvent_t e;
+    CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), return fail());
+    c->evRun.push_back(e);
+  }
+  size_t piece = 0;
+  for (size_t gi = 0; gi < groups.size(); gi++) {
+    const Group &g = groups[gi];
+    while (piece + 1 < fl.ends.size() && fl.ends[piece] < g.needEnd) piece++;
+    CU_TRY(cudaStreamWaitEvent(c->sRun, c->evIn[piece], 0), return fail());
+    int rc;
+    if (family == HSR_BLOCK)
+      rc = launch_block_batch(N, bits, c->dIn, c->dOut, reinterpret_cast<const BlockStreamDesc *>(c->dBlocks) + g.sa, (uint32_t)(g.sb - g.sa),
+                              c->dCounters, c->hStatus + g.sa, c->sRun, g.decoded);
+    else
+      rc = launch_units(family, N, bits, c->dIn, inLo, c->dOut, outLo, c->dBlocks + g.ua, (uint32_t)(g.ub - g.ua), c->dCounters + 1, c->sRun,
+                        c->hStatus, g.decoded);
+    if (rc < 0) return fail();
+    CU_TRY(cudaEventRecord(c->evRun[gi], c->sRun), return fail());
+    g_trace.mark("run end", gi, g.decoded, c->sRun);
+  }
+
+  // as each group finishes: copy back the streams that decoded cleanly, merging runs whose outputs are contiguous
   size_t ok = 0;
-  if (family == HSR_BLOCK) {
-    std::vector<uint32_t> perStream(count, 0);
-    for (size_t k = 0; k < descStream.size(); k++) perStream[descStream[k]] = status[4 + k];
-    for (size_t i = 0; i < count; i++) status[4 + i] = perStream[i];
+  for (size_t gi = 0; gi < groups.size(); gi++) {
+    const Group &g = groups[gi];
+    CU_TRY(cudaEventSynchronize(c->evRun[gi]), return fail());
+    uint64_t runLo = 0, runHi = 0;
+    bool open = false;
+    auto flush = [&]() -> bool {
+      if (!open) return true;
+      CU_TRY(cudaMemcpyAsync(outBase + runLo, c->dOut + (runLo - outLo), (size_t)(runHi - runLo), cudaMemcpyDeviceToHost, c->sOut), return false);
+      g_trace.mark("d2h end", gi, runHi - runLo, c->sOut);
+      open = false;
+      return true;
+    };
+    for (size_t k = g.sa; k < g.sb; k++) {
+      const uint32_t i = order[k];
+      const uint32_t st = family == HSR_BLOCK ? c->hStatus[k] : c->hStatus[i];
+      if (st) continue;
+      decodedLengths[i] = hdr[i].n;
+      ok++;
+      const uint64_t lo = items[i].outOffset, hi = lo + hdr[i].n;
+      if (open && lo == runHi) { runHi = hi; continue; }
+      if (!flush()) return fail();
+      runLo = lo; runHi = hi; open = true;
+    }
+    if (!flush()) return fail();
   }
-  uint64_t runLo = 0, runHi = 0;
-  bool open = false;
-  auto flush = [&]() -> bool {
-    if (!open) return true;
-    CU_TRY(cudaMemcpyAsync(outBase + runLo, c->dOut + (runLo - outLo), (size_t)(runHi - runLo), cudaMemcpyDeviceToHost, c->sOut), return false);
-    open = false;
-    return true;
-  };
-  for (size_t i = 0; i < count; i++) {
-    if (!good[i] || status[4 + i]) continue;
-    decodedLengths[i] = hdr[i].n;
-    ok++;
-    const uint64_t lo = items[i].outOffset, hi = lo + hdr[i].n;
-    if (open && lo == runHi) { runHi = hi; continue; }
-    if (!flush()) return 0;
-    runLo = lo; runHi = hi; open = true;
-  }
-  if (!flush()) return 0;
-  CU_TRY(cudaStreamSynchronize(c->sOut), return 0);
+  CU_TRY(cudaStreamSynchronize(c->sOut), return fail());
+  CU_TRY(cudaStreamSynchronize(c->sIn), return fail());
+  g_trace.dump();
   if (ok != count) set_err("%zu of %zu streams were malformed", count - ok, count);
   return ok;
 }

@@ -53,7 +53,9 @@ const char *hsr_last_error(void);
  *   "overlap"    1 (default) = consecutive decode launches on one CUDA stream overlap: the next launch's warps take
  *                over SM slots as the previous launch drains (programmatic dependent launch); 0 = strictly serial
  *   "contexts"   host-pointer decodes that may be in flight per device at once (1..16, default 4); each holds its
- *                own streams and device scratch, further callers wait                                              */
+ *                own streams and device scratch, further callers wait
+ *   "batch_group_mb"  hsr_decode_batch: traffic per pipeline group in MiB (0 = auto: enough bytes per group for its
+ *                copies to outlast the one-warp decode time of its longest stream; tests)                           */
 int hsr_set_option(const char *key, long value);
 long hsr_get_option(const char *key);
 

@@ -299,3 +299,56 @@ def test_hostile_header_lengths_are_refused(gpu, golden):
         gpu.PreparedStream.upload(ck.MT, 64, 11, stream)
     with pytest.raises(gpu.HsrError):
         gpu.mt_index(64, stream)
+
+
+@pytest.mark.parametrize("fam", [ck.RAW, ck.BLOCK, ck.MT])
+def test_batch_pipeline_many_groups_any_order(gpu, fam):
+    """hsr_decode_batch runs as a pipeline of stream groups (6, 12, 24, 48 ... MiB of traffic each): enough streams for
+    several groups, handed over in shuffled order with outputs laid out in yet another order, one stream corrupted —
+    every clean stream must arrive byte-exact, the corrupted one must fail alone and leave its output untouched."""
+    if not ck.have_ref():
+        pytest.skip("needs oracle/_ref")
+    states, bits = {ck.RAW: (32, 11), ck.BLOCK: (64, 13), ck.MT: (64, 15)}[fam]
+    rng = np.random.default_rng(5)
+    k, each = 60, 300_000
+    datas = [ck.synth_zipf(each + int(rng.integers(0, 5000)), 1.0, seed=300 + i, segment_bytes=65536) for i in range(k)]
+    streams = [ck.ref_encode(fam, states, bits, d) for d in datas]
+    bad = 17
+    streams[bad] = streams[bad].copy()
+    off = {ck.RAW: 16 + 9, ck.BLOCK: 16 + 4 * states + 8 + 9, ck.MT: 16 + 16 + 4 * states + 9}[fam]
+    streams[bad][off] ^= 0x40
+    in_order = rng.permutation(k)     # where each stream sits in the input buffer
+    out_order = rng.permutation(k)    # ... and in the output buffer
+    in_off, pos = {}, 0
+    parts = []
+    for i in in_order:
+        pad = (-pos) % 16
+        parts.append(np.zeros(pad, np.uint8)); pos += pad
+        in_off[i] = pos
+        parts.append(streams[i]); pos += streams[i].size
+    in_base = np.concatenate(parts)
+    out_off, pos = {}, 0
+    for i in out_order:
+        out_off[i] = pos
+        pos += datas[i].size + 5
+    out_base = np.full(pos + 64, 0xCC, np.uint8)
+    items = [(in_off[i], streams[i].size, out_off[i], datas[i].size) for i in range(k)]
+    hin, hout = gpu.host_alloc(in_base.size), gpu.host_alloc(out_base.size)
+    hin.array[:] = in_base
+    hout.array[:] = out_base
+    try:
+        for group_mb in (4, 1, 0):    # 9 groups, ~33 groups, automatic (one group for streams this short)
+            gpu.set_option("batch_group_mb", group_mb)
+            hout.array[:] = 0xCC
+            ok, lengths = gpu.decode_batch(fam, states, bits, hin.array, hout.array, items)
+            assert ok == k - 1, (group_mb, gpu.last_error())
+            for i in range(k):
+                o, n = out_off[i], datas[i].size
+                if i == bad:
+                    assert lengths[i] == 0 and np.all(hout.array[o:o + n] == 0xCC), group_mb
+                    continue
+                assert lengths[i] == n and np.array_equal(hout.array[o:o + n], datas[i]), (group_mb, i)
+                assert np.all(hout.array[o + n:o + n + 5] == 0xCC), (group_mb, i)
+    finally:
+        gpu.set_option("batch_group_mb", 0)
+        hin.free(); hout.free()
