@@ -52,4 +52,23 @@ for states, bits in ((32, 10), (64, 15)):
         ok = n == data.size and np.array_equal(out[:n], data)
         bad += not ok
         print("encoder", fn.__name__, states, bits, "ok" if ok else "MISMATCH")
+# round 2: the pipelined batch entry point (groups, per-stream status in mapped host memory), one stream corrupted
+for fam, states, bits in ((0, 64, 12), (1, 32, 10), (2, 64, 15)):
+    key = f"stream/multi/{fam}/{states}/{bits}"
+    streams = [z[key].copy() for _ in range(6)]
+    streams[2][16 + (16 + 4 * states if fam == 2 else (4 * states + 8 if fam == 1 else 0)) + 9] ^= 0x40
+    src = z["in/multi"]
+    parts, items, pos = [], [], 0
+    for k, st in enumerate(streams):
+        pad = (-pos) % 16
+        parts.append(np.zeros(pad, np.uint8)); pos += pad
+        items.append((pos, st.size, k * (src.size + 3), src.size))
+        parts.append(st); pos += st.size
+    out_base = np.full(6 * (src.size + 3) + 64, 0xCC, np.uint8)
+    pkg.set_option("batch_group_mb", 1)
+    ok, lengths = pkg.decode_batch(fam, states, bits, np.concatenate(parts), out_base, items)
+    pkg.set_option("batch_group_mb", 0)
+    good = ok == 5 and lengths[2] == 0 and all(np.array_equal(out_base[k * (src.size + 3): k * (src.size + 3) + src.size], src) for k in (0, 1, 3, 4, 5))
+    bad += not good
+    print("batch", fam, states, bits, "ok" if good else "MISMATCH", ok)
 sys.exit(1 if bad else 0)
