@@ -53,9 +53,12 @@ def assemble_on(dst: int, local, plans: Sequence[ShardPlan], total_bytes: int, g
     rank = dist.get_rank(group)
     if rank != dst:
         if plans[rank].out_bytes:
-            dist.send(local[: plans[rank].out_bytes].contiguous(), dst=dst, group=group)
+            op = dist.P2POp(dist.isend, local[: plans[rank].out_bytes].contiguous(), dst, group)
+            for req in dist.batch_isend_irecv([op]):
+                req.wait()
         return None
     full = torch.empty(total_bytes, dtype=torch.uint8, device=local.device)
+    ops = []  # every receive is posted at once (one NCCL group): the shards arrive side by side over NVLink
     for p in plans:
         if p.out_bytes == 0:
             continue
@@ -63,5 +66,8 @@ def assemble_on(dst: int, local, plans: Sequence[ShardPlan], total_bytes: int, g
         if p.rank == dst:
             view.copy_(local[: p.out_bytes])
         else:
-            dist.recv(view, src=p.rank, group=group)
+            ops.append(dist.P2POp(dist.irecv, view, p.rank, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
     return full
