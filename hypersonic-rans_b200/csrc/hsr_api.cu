@@ -742,7 +742,7 @@ static hsr_stream_t *stream_from_device_impl(int family, int N, int bits, const 
     for (size_t k = 0; k < numUnits; k++) {
       const hsr_block_t &b = s->blocks[k];
       const bool coded = b.kind == 0;
-      const bool ok = (b.kind == 0 || b.kind == 1) && (b.inOffset & 1ull) == 0 && b.inOffset >= 16 && b.inEnd <= h.compLen &&
+      const bool ok = (b.kind == 0 || b.kind == 1) && (b.inOffset & 1ull) == 0 && b.inOffset >= 16 && b.inOffset < b.inEnd && b.inEnd <= h.compLen &&
                       b.inOffset + (coded ? 4ull * N + 512 : 8ull) <= b.inEnd && b.inEnd - b.inOffset <= kMaxUnitIn && b.outOffset == at &&
                       b.count <= h.n - at && b.tail < (uint32_t)N && (coded ? (b.count - b.tail) % (uint64_t)N == 0 && b.count >= b.tail : b.tail == 0) &&
                       (b.tail == 0 || at + b.count == h.n);
@@ -768,19 +768,19 @@ static hsr_stream_t *stream_from_device_impl(int family, int N, int bits, const 
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int attempt = 0; attempt < 2; attempt++) {
       hsr_block_t *dB = nullptr;
-      CU_TRY(cudaMalloc(&dB, cap * sizeof(hsr_block_t)), { cudaFree(dRes); return nullptr; });
+      CU_TRY(cudaMalloc(&dB, cap * sizeof(hsr_block_t)), { cudaFree(dRes); cudaEventDestroy(e0); cudaEventDestroy(e1); return nullptr; });
       cudaEventRecord(e0);
       mt_walk_kernel<<<1, 32>>>(dIn, h.compLen, (uint32_t)N, dB, cap, dRes);
       cudaEventRecord(e1);
       unsigned long long res[2] = {0, 0};
-      CU_TRY(cudaMemcpy(res, dRes, 16, cudaMemcpyDeviceToHost), { cudaFree(dB); cudaFree(dRes); return nullptr; });
+      CU_TRY(cudaMemcpy(res, dRes, 16, cudaMemcpyDeviceToHost), { cudaFree(dB); cudaFree(dRes); cudaEventDestroy(e0); cudaEventDestroy(e1); return nullptr; });
       float ms = 0;
       cudaEventElapsedTime(&ms, e0, e1);
       s->indexMs += ms;
-      if (res[1]) { set_err("malformed mt_ chain (device walk error %llu)", res[1]); cudaFree(dB); cudaFree(dRes); return nullptr; }
+      if (res[1]) { set_err("malformed mt_ chain (device walk error %llu)", res[1]); cudaFree(dB); cudaFree(dRes); cudaEventDestroy(e0); cudaEventDestroy(e1); return nullptr; }
       if (res[0] <= cap) {
         s->blocks.resize((size_t)res[0]);
-        CU_TRY(cudaMemcpy(s->blocks.data(), dB, s->blocks.size() * sizeof(hsr_block_t), cudaMemcpyDeviceToHost), { cudaFree(dB); cudaFree(dRes); return nullptr; });
+        CU_TRY(cudaMemcpy(s->blocks.data(), dB, s->blocks.size() * sizeof(hsr_block_t), cudaMemcpyDeviceToHost), { cudaFree(dB); cudaFree(dRes); cudaEventDestroy(e0); cudaEventDestroy(e1); return nullptr; });
         cudaFree(dB);
         break;
       }
@@ -1352,7 +1352,11 @@ static size_t decode_batch_impl(int family, int N, int bits, const uint8_t *inBa
     }
   }
 
-  auto fail = [&]() -> size_t { cudaStreamSynchronize(c->sIn); cudaStreamSynchronize(c->sRun); cudaStreamSynchronize(c->sOut); return 0; };
+  auto fail = [&]() -> size_t { // a CUDA call failed: drain what is in flight and report nothing decoded
+    cudaStreamSynchronize(c->sIn); cudaStreamSynchronize(c->sRun); cudaStreamSynchronize(c->sOut);
+    for (size_t i = 0; i < count; i++) decodedLengths[i] = 0;
+    return 0;
+  };
   // the unit list goes up FIRST: a copy queued behind the input pieces would wait for all of them on the copy engine
   // (and with it every launch: measured, the first group then starts after the whole 14 ms of input)
   const size_t listBytes = family == HSR_BLOCK ? sd.size() * sizeof(BlockStreamDesc) : su.size() * sizeof(hsr_block_t);

@@ -234,6 +234,13 @@ def test_encoder_block_table_skips_the_chain_walk(gpu):
         idx[:48] = torch.from_numpy(rec).cuda()
         with pytest.raises(gpu.HsrError):
             gpu.PreparedStream.from_device_indexed(states, bits, d_out.data_ptr(), comp, idx.data_ptr(), units)
+        # an inOffset just below 2^64 makes inOffset + header wrap around to a small number: must be refused as well
+        rec = d_idx[:48].cpu().numpy().copy()
+        rec[0:8] = np.frombuffer(np.uint64(2**64 - 8).tobytes(), np.uint8)
+        idx = d_idx.clone()
+        idx[:48] = torch.from_numpy(rec).cuda()
+        with pytest.raises(gpu.HsrError):
+            gpu.PreparedStream.from_device_indexed(states, bits, d_out.data_ptr(), comp, idx.data_ptr(), units)
         ps.free(); walked.free()
 
 
