@@ -678,6 +678,44 @@ def main():
         wps.free()
         del wout
 
+    # ---------------------------------------------------------------- block_ at N > 1: replicas only
+    # A block_ (or raw) stream is one recurrence and does not shard; what spreads over GPUs is a BATCH of streams, every
+    # rank decoding its own replica of the batch with no exchange at all. Reported so the N-GPU line carries the block_
+    # variant too: aggregate = N x the slowest rank's rate.
+    block_replicas = None
+    if world > 1 and not a.headline_only and not a.kernel_only:
+        import checkers as ck
+        _stage('block_ batch replicas')
+        k_streams, each = 2368, 400_000     # 16 streams per SM, the batch of `other_configs` at N = 1
+        bdata = make_data(a, seed=900 + rank, size=k_streams * each, shape="iid")
+        parts, items, pos = [], [], 0
+        for k in range(k_streams):
+            bs = ck.ref_encode(FAMILY_BLOCK, 32, 10, bdata[k * each:(k + 1) * each])
+            pad = (-pos) % 16
+            parts.append(np.zeros(pad, np.uint8)); pos += pad
+            items.append((pos, bs.size, k * each, each))
+            parts.append(bs); pos += bs.size
+        bps = pkg.PreparedStream.upload_batch(FAMILY_BLOCK, 32, 10, np.concatenate(parts), items)
+        btotal = k_streams * each
+        bout = torch.empty(btotal + 64, dtype=torch.uint8, device="cuda")
+        bps.decode_async(bout.data_ptr(), btotal, cur)
+        torch.cuda.synchronize()
+        b_ok = bps.status() == 0 and bool(np.array_equal(bout[:btotal].cpu().numpy(), bdata))
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(5):
+            bps.decode_async(bout.data_ptr(), btotal, cur)
+        b1.record()
+        barrier()
+        bms = max_over_ranks(b0.elapsed_time(b1) / 5)
+        all_ok = min_over_ranks(1.0 if b_ok else 0.0) > 0.5
+        block_replicas = {"value": round(world * btotal / bms / 1e6, 2), "unit": "GB/s", "codec": "block_rANS32x32_16w 10-bit",
+                          "streams_per_gpu": k_streams, "bytes_per_stream": each, "ms_per_step": round(bms, 4), "bit_exact_on_every_rank": all_ok,
+                          "note": "replicas only: every rank decodes its own batch of independent block_ streams, no exchange"}
+        bps.free()
+        del bout
+
     if rank == 0:
         # ---------------------------------------------------------------- index timings (reported apart, SURVEY §8d "I")
         _stage('index timings')
@@ -737,6 +775,8 @@ def main():
             line["e2e_one_process_per_gpu"] = e2e_shards
         if weak:
             line["weak_scaling"] = weak
+        if block_replicas:
+            line["block_replicas"] = block_replicas
         _stage('cpu baseline')
         if not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a, stream, n)
