@@ -254,6 +254,41 @@ __global__ void __launch_bounds__(1024) enc_scan_kernel(const EncBlockMeta *meta
 
 __device__ __forceinline__ void st_u16(uint8_t *p, uint32_t v) { *reinterpret_cast<uint16_t *>(p) = (uint16_t)v; }
 
+// Moves `bytes` (even) of 16-bit words from src to dst, both only 2-byte aligned and misaligned against each other in
+// general (the header in front of the words is 16 + 4N + 512 bytes, the scratch slot ends wherever the block's words
+// began). dst is brought to a 16-byte boundary with single words; from there every thread writes one aligned 16-byte
+// vector assembled from five consecutive 4-byte-aligned source words by funnel shifts (the source is off by 0 or 2
+// bytes against a 4-byte grid) — 6 memory instructions per 16 bytes instead of 16. The fifth word of the last vector
+// may lie up to 4 bytes past the block's words: inside the scratch allocation (its slots are contiguous and it carries
+// slack at the end), read but never stored.
+__device__ __forceinline__ void cta_move_words(uint8_t *dst, const uint8_t *src, uint32_t bytes, uint32_t tid, uint32_t threads)
+{
+  uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
+  if (head > bytes) head = bytes;
+  for (uint32_t i = tid; i < head / 2; i += threads)
+    st_u16(dst + 2 * i, *reinterpret_cast<const uint16_t *>(src + 2 * i));
+  dst += head; src += head; bytes -= head;
+  const uint32_t vecs = bytes / 16;
+  const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);      // 0 or 2
+  const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src - off);
+  const uint32_t sh = off * 8u;
+  uint4 *d16 = reinterpret_cast<uint4 *>(dst);
+  for (uint32_t v = tid; v < vecs; v += threads) {
+    const uint32_t *p = s4 + 4 * v;
+    const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3);
+    uint4 o;
+    if (off) {
+      const uint32_t w4 = __ldg(p + 4);
+      o = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    } else
+      o = make_uint4(w0, w1, w2, w3);
+    d16[v] = o;
+  }
+  const uint32_t done = vecs * 16;
+  for (uint32_t i = tid; i < (bytes - done) / 2; i += threads)
+    st_u16(dst + done + 2 * i, *reinterpret_cast<const uint16_t *>(src + done + 2 * i));
+}
+
 template <int N>
 __global__ void __launch_bounds__(256, 8) enc_assemble_kernel(EncPlan pl, const uint16_t *counts, const uint8_t *scratch, const EncBlockMeta *meta,
                                                            const uint64_t *offsets, uint8_t *out, hsr_block_t *index)
@@ -300,10 +335,7 @@ __global__ void __launch_bounds__(256, 8) enc_assemble_kernel(EncPlan pl, const 
       st_u16(dst + 16 + 2 * i, meta[k].states[i >> 1] >> (16 * (i & 1)));
     for (uint32_t i = tid; i < 256; i += blockDim.x)
       st_u16(dst + 16 + 4 * N + 2 * i, counts[(uint64_t)k * 256 + i]);
-    const uint8_t *src = scratch + slot_end(pl, k) - wordBytes;
-    uint8_t *wdst = dst + kHeader;
-    for (uint32_t i = tid; i < wordBytes / 2; i += blockDim.x)
-      st_u16(wdst + 2 * i, *reinterpret_cast<const uint16_t *>(src + 2 * i));
+    cta_move_words(dst + kHeader, scratch + slot_end(pl, k) - wordBytes, wordBytes, tid, blockDim.x);
   }
 }
 
