@@ -112,7 +112,13 @@ int hsr_set_device(int device);
  * inBase[inOffset, inOffset + inLength) and decodes to outBase[outOffset, outOffset + n) with n <= outCapacity;
  * inOffset must be even (streams are sequences of 16-bit words; an odd one marks the stream malformed); output ranges
  * must not overlap. decodedLengths[i] receives n, or 0 if stream i is malformed (the others are still
- * decoded). Returns the number of streams decoded. Each stream is checked like hsr_decode checks its input. */
+ * decoded; the output range of a malformed stream is left untouched). Returns the number of streams decoded. Each
+ * stream is checked like hsr_decode checks its input. The call is a pipeline: the input range goes to the device in
+ * pieces, groups of streams (in input order) are launched as their bytes land, and their decoded bytes return while
+ * later groups decode.
+ *
+ * Diagnostics: with the environment variable HSR_TRACE_PIPELINE set, hsr_decode (mt_) and hsr_decode_batch print the
+ * device timestamps of every copy piece, launch and copy-back of the call to stderr. */
 
 size_t hsr_decode_batch(int family, int stateCount, int bits, const uint8_t *inBase, uint8_t *outBase,
                         const hsr_batch_item_t *items, size_t count, uint64_t *decodedLengths);
